@@ -1,0 +1,171 @@
+/* nwk.h -- C ABI of the B200-native exact brute-force kNN engine (libnwk.so).
+ *
+ * This is the drop-in boundary for neighborhoodwatch's ground-truth hot path.  The
+ * reference has no FFI layer of its own (it is pure Python calling RAPIDS / torch), so
+ * every entry point below replaces a library call site or a Python function of the
+ * reference; the file:line each one stands in for is cited beside it (paths relative to
+ * /root/reference/).  INTEGRATION.md shows the ctypes stubs a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes only; no C++ or torch types cross the boundary.
+ *   - Every function returns 0 on success and a non-zero nwk_status otherwise;
+ *     nwk_last_error() returns a thread-local human-readable message for the last failure.
+ *   - All matrix arguments are dense row-major (C order) fp32, the layout the reference
+ *     produces with cupy ``.copy(order='C')`` (neighborhoodwatch/cu_knn.py:211,235).
+ *   - Unless a parameter is documented as HOST memory, pointers are DEVICE addresses valid
+ *     on the current CUDA device.  The caller owns every buffer; the library allocates only
+ *     inside opaque handles (nwk_topk_state) that it also frees.
+ *   - ``stream`` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *     Calls enqueue work on that stream; nwk_knn_f32 additionally synchronises the stream
+ *     before returning (the reference is synchronous too: every knn() is followed by
+ *     ``.get()``, cu_knn.py:271) because it must read back the per-query certification
+ *     counters to decide whether the exact fallback pass is needed.
+ *   - There is no CPU fallback: on a machine without an sm_100 device every compute entry
+ *     point fails with NWK_ERR_DEVICE.
+ */
+#ifndef NWK_H_
+#define NWK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NWK_ABI_VERSION 1
+
+typedef enum nwk_status {
+  NWK_OK = 0,
+  NWK_ERR_ARG = 1,        /* bad argument (null pointer, k > rows, d == 0, ...)       */
+  NWK_ERR_CUDA = 2,       /* a CUDA runtime / driver call failed                      */
+  NWK_ERR_WORKSPACE = 3,  /* workspace smaller than nwk_knn_workspace_bytes()         */
+  NWK_ERR_DEVICE = 4,     /* no sm_100 device, or the kernel image cannot run here    */
+  NWK_ERR_INTERNAL = 5    /* an internal invariant failed (kernel watchdog, overflow) */
+} nwk_status;
+
+/* Distance definitions (selected in the reference by the ``engine`` argument of
+ * process_batches, cu_knn.py:242-262):
+ *   NWK_METRIC_SQEUCLIDEAN  sum_i (q_i - b_i)^2          engine 'raft'  cu_knn.py:243-245
+ *   NWK_METRIC_COSINE       1 - q.b / (|q| |b|)          engine 'cuvs'  cu_knn.py:247-248
+ *   NWK_METRIC_DOT          1 - q.b                      engine 'torch' cu_knn.py:256     */
+typedef enum nwk_metric {
+  NWK_METRIC_SQEUCLIDEAN = 0,
+  NWK_METRIC_COSINE = 1,
+  NWK_METRIC_DOT = 2
+} nwk_metric;
+
+/* flags for nwk_knn_f32 / nwk_knn_host_f32 */
+#define NWK_FLAG_FORCE_EXACT_SCAN 0x1u /* skip the tensor-core candidate stage; fp64 scan of every pair */
+#define NWK_FLAG_NO_FALLBACK      0x2u /* do not run the fp64 scan for uncertified queries (diagnostics) */
+#define NWK_FLAG_PROFILE          0x4u /* bracket each stage with CUDA events on `stream`; fills stats->ms_*  */
+
+/* Per-call diagnostics (all counters refer to the last nwk_knn_f32 call they were passed to). */
+typedef struct nwk_knn_stats {
+  int32_t path;               /* 0 = fp64 exact scan, 1 = tcgen05 TF32 candidates + fp64 rerank          */
+  int32_t n_fallback_queries; /* queries whose candidate set could not be certified -> fp64 exact scan   */
+  int32_t max_candidates;     /* largest per-query candidate-log population seen                         */
+  int32_t max_rerank;         /* largest per-query number of rows re-ranked in fp64                      */
+  int64_t total_candidates;   /* sum over queries of candidate-log population                            */
+  int64_t total_rerank;       /* sum over queries of rows re-ranked in fp64                              */
+  int32_t gpu_launches;       /* kernels launched by this call                                           */
+  int32_t reserved;
+  /* device time per stage, CUDA events on the caller's stream; 0 unless NWK_FLAG_PROFILE */
+  float   ms_rownorm;         /* base row norms (HBM-bound)                                              */
+  float   ms_sample;          /* tcgen05 sample pass -> per-query thresholds                             */
+  float   ms_filter;          /* tcgen05 filter pass over the whole base: the dominant kernel            */
+  float   ms_finish;          /* select + fp64 rerank                                                    */
+  float   ms_fallback;        /* fp64 scan of uncertified queries                                        */
+  float   ms_total;           /* whole call                                                              */
+} nwk_knn_stats;
+
+const char* nwk_last_error(void);
+int nwk_abi_version(void);
+
+/* Number of kernels this library has launched in the calling process (bench.py's
+ * ``gpu_launches`` is the difference of two readings). */
+int64_t nwk_launch_count(void);
+
+/* Exact k nearest neighbours of every query row among the base rows.
+ *
+ * Replaces the array-level operator of the reference:
+ *   pylibraft.neighbors.brute_force.knn(dataset, queries, k)   cu_knn.py:243-245, cu_knn_ds.py:213
+ *   cuvs.neighbors.brute_force.build(...)/search(...)          cu_knn.py:247-248
+ *   1 - torch.matmul(q, b.T); torch.topk(.., largest=False)    cu_knn.py:256-257
+ * and folds in the ``indices + batch_offset`` step of cu_knn.py:273 through ``id_offset``.
+ *
+ *   base      [nb, d] fp32 row-major, device
+ *   query     [nq, d] fp32 row-major, device
+ *   out_dist  [nq, k] fp32, ascending per row
+ *   out_idx   [nq, k] int64, row index into base + id_offset
+ *   workspace device scratch of at least nwk_knn_workspace_bytes(...) bytes, 256-byte aligned
+ *   stats     optional (may be NULL), HOST memory
+ *
+ * Results are exact: candidates are produced on the tensor cores in TF32, every candidate
+ * within a proven error bound of the k-th is re-ranked in fp64, and queries for which the
+ * bound cannot be established are recomputed by an fp64 scan.  Ordering is by
+ * (fp64 distance, index).  Fails with NWK_ERR_ARG when k > nb (the reference asserts
+ * ``k <= len(dataset)``, cu_knn.py:237) or k > NWK_MAX_K. */
+#define NWK_MAX_K 1024
+size_t nwk_knn_workspace_bytes(int64_t nb, int64_t nq, int32_t d, int32_t k, int32_t metric,
+                               uint32_t flags);
+int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d,
+                int32_t k, int32_t metric, int64_t id_offset, float* out_dist, int64_t* out_idx,
+                void* workspace, size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats,
+                void* stream);
+
+/* Merge P sorted partial results into the k_out best per query, ordered by
+ * (distance, index).  Replaces merge_indices_and_distances' argsort fold, merge.py:73-104,
+ * and is the cross-GPU / cross-slab reducer.
+ *
+ *   dist  [P, nq, k_in] fp32 device (partial p, query q, slot j at ((p*nq)+q)*k_in + j)
+ *   idx   [P, nq, k_in] int64 device, global row ids
+ *   out_dist [nq, k_out] fp32, out_idx [nq, k_out] int64; requires k_out <= P*k_in
+ *   workspace: nwk_merge_workspace_bytes(P, nq, k_in, k_out) bytes of device scratch */
+size_t nwk_merge_workspace_bytes(int32_t P, int64_t nq, int32_t k_in, int32_t k_out);
+int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq, int32_t k_in,
+                   int32_t k_out, float* out_dist, int64_t* out_idx, void* workspace,
+                   size_t ws_bytes, void* stream);
+
+/* Running per-query top-k across base slabs: the intended semantics of the streaming
+ * driver, cu_knn_ds.py:181-239 (one global result over all base batches), and the
+ * reducer compute_knn uses instead of writing P partial files when asked to.
+ * update() merges one [nq, k] partial (device pointers) into the state; finalize() copies
+ * the current result out.  The handle owns its device memory. */
+typedef struct nwk_topk_state nwk_topk_state;
+int nwk_topk_state_create(int64_t nq, int32_t k, nwk_topk_state** out);
+int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* idx, void* stream);
+int nwk_topk_state_finalize(nwk_topk_state* st, float* out_dist, int64_t* out_idx, void* stream);
+int nwk_topk_state_destroy(nwk_topk_state* st);
+
+/* Host-buffer entry point (what `e2e` in bench.py times): base and query are HOST
+ * pointers (pinned memory gives full PCIe rate); the base is cut into slabs of
+ * ``slab_rows`` rows that are copied on a side stream into a two-deep device ring while
+ * the previous slab is searched; results are written to HOST out_dist / out_idx.
+ * Replaces the load + loop of compute_knn_ds / process_dataset_batches
+ * (cu_knn_ds.py:136-239) and of compute_knn / process_batches (cu_knn.py:151-287) for
+ * callers that hold the vectors in host memory.  slab_rows == 0 picks a default. */
+int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host, int64_t nq,
+                     int32_t d, int32_t k, int32_t metric, int64_t id_offset, int64_t slab_rows,
+                     float* out_dist_host, int64_t* out_idx_host, uint32_t flags,
+                     nwk_knn_stats* stats);
+
+/* Deterministic synthetic vectors (the fixture style of tests/test_02_cu_knn.py:21-28:
+ * uniform[0,1) components, rows L2-normalised), counter-based so any slab of a large base
+ * can be regenerated: element (row, col) depends only on (seed, row, col, d).  The numpy
+ * twin is neighborhoodwatch_b200/synth.py.  out is [rows, d] fp32 device memory holding
+ * rows row0 .. row0+rows-1. */
+int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0,
+                   int32_t normalize, void* stream);
+
+/* Diagnostics used by the parity tests: raw TF32 tensor-core dot products of one
+ * 128 x 256 tile pair (query rows q0.., base rows b0..) written to out[128*256] fp32,
+ * so the tcgen05 / TMA descriptors can be validated in isolation. */
+int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d,
+                      int64_t b0, int64_t q0, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWK_H_ */

@@ -1,0 +1,382 @@
+// nwk_api.cu -- the extern "C" surface declared in include/nwk.h.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "nwk_common.cuh"
+
+namespace nwk {
+
+// implemented in the other translation units
+int exact_scan(const float* base, long long nb, const float* query, int d, int k, int metric,
+               long long id_offset, const int* qsel, long long nsel, float* out_dist,
+               long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t exact_scan_workspace_bytes(long long nb, long long nsel, int k);
+size_t merge_workspace_bytes(int P, long long nq, int k_in, int k_out);
+int merge_topk(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
+               float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+bool tc_path_supported(long long nb, long long nq, int d, int k);
+size_t tc_workspace_bytes(long long nb, long long nq, int d, int k);
+int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
+           long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
+           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s);
+int tc_debug_tile(const float* base, long long nb, const float* query, long long nq, int d, long long b0,
+                  long long q0, float* out, cudaStream_t s);
+int synth_fill(float* out, long long rows, int d, unsigned long long seed, long long row0, int normalize,
+               cudaStream_t s);
+
+std::atomic<long long> g_launches{0};
+
+std::string& last_error_ref() {
+  static thread_local std::string msg;
+  return msg;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+static int g_sm_count = 0;
+
+int device_check() {
+  static int cached = -1;      // -1 unknown, 0 ok
+  if (cached == 0) return NWK_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return fail(NWK_ERR_DEVICE, "no CUDA device available: %s (this library has no CPU fallback)",
+                cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(NWK_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(NWK_ERR_DEVICE, "device %d (%s) is sm_%d%d; libnwk is built for sm_100a only", dev, prop.name,
+                prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  cached = 0;
+  return NWK_OK;
+}
+
+int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+static bool want_tc(long long nb, long long nq, int d, int k, unsigned int flags) {
+  if (flags & NWK_FLAG_FORCE_EXACT_SCAN) return false;
+  if (getenv("NWK_FORCE_EXACT_SCAN")) return false;
+  return tc_path_supported(nb, nq, d, k);
+}
+
+}  // namespace nwk
+
+using namespace nwk;
+
+__global__ void state_init_kernel(float* d, long long* i, long long n) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    d[t] = __int_as_float(0x7f800000);
+    i[t] = -1;
+  }
+}
+
+// Process-wide cache of the device staging buffers so repeated calls do not pay cudaMalloc.
+namespace {
+struct HostCtx {
+  std::mutex mu;
+  float* slab[2] = {nullptr, nullptr};
+  size_t slab_bytes = 0;
+  float* query = nullptr;
+  size_t query_bytes = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* part_d = nullptr;
+  long long* part_i = nullptr;
+  size_t part_n = 0;
+  cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  bool init = false;
+};
+HostCtx g_host;
+
+template <typename T>
+int grow(T** p, size_t* have, size_t want) {
+  if (*have >= want) return NWK_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  *have = want;
+  return NWK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* nwk_last_error(void) { return last_error_ref().c_str(); }
+int nwk_abi_version(void) { return NWK_ABI_VERSION; }
+int64_t nwk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t nwk_knn_workspace_bytes(int64_t nb, int64_t nq, int32_t d, int32_t k, int32_t metric, uint32_t flags) {
+  (void)metric;
+  if (nb <= 0 || nq <= 0 || d <= 0 || k <= 0) return 256;
+  if (want_tc(nb, nq, d, k, flags)) return tc_workspace_bytes(nb, nq, d, k);
+  return exact_scan_workspace_bytes(nb, nq, k) + 256;
+}
+
+int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int32_t k,
+                int32_t metric, int64_t id_offset, float* out_dist, int64_t* out_idx, void* workspace,
+                size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats, void* stream) {
+  if (!base || !query || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (nb <= 0 || nq < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad shape nb=%lld nq=%lld d=%d", (long long)nb, (long long)nq, d);
+  if (k <= 0 || k > NWK_MAX_K) return fail(NWK_ERR_ARG, "k=%d outside [1, %d]", k, NWK_MAX_K);
+  if (k > nb) return fail(NWK_ERR_ARG, "k=%d exceeds dataset rows %lld", k, (long long)nb);
+  if (metric < 0 || metric > 2) return fail(NWK_ERR_ARG, "unknown metric %d", metric);
+  if (nb >= (1ll << 31)) return fail(NWK_ERR_ARG, "nb=%lld: at most 2^31-1 base rows per call", (long long)nb);
+  NWK_TRY(device_check());
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (nq == 0) return NWK_OK;
+  if (ws_bytes < nwk_knn_workspace_bytes(nb, nq, d, k, metric, flags) || !workspace)
+    return fail(NWK_ERR_WORKSPACE, "workspace of %zu bytes is smaller than nwk_knn_workspace_bytes() = %zu",
+                ws_bytes, nwk_knn_workspace_bytes(nb, nq, d, k, metric, flags));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (want_tc(nb, nq, d, k, flags))
+    return tc_knn(base, nb, query, nq, d, k, metric, id_offset, out_dist, (long long*)out_idx, workspace,
+                  ws_bytes, flags, stats, s);
+  const long long l0 = g_launches.load();
+  NWK_TRY(exact_scan(base, nb, query, d, k, metric, id_offset, nullptr, nq, out_dist, (long long*)out_idx,
+                     workspace, ws_bytes, s));
+  NWK_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->path = 0;
+    stats->gpu_launches = (int)(g_launches.load() - l0);
+  }
+  return NWK_OK;
+}
+
+size_t nwk_merge_workspace_bytes(int32_t P, int64_t nq, int32_t k_in, int32_t k_out) {
+  if (P <= 0 || nq <= 0 || k_in <= 0 || k_out <= 0) return 256;
+  return merge_workspace_bytes(P, nq, k_in, k_out);
+}
+
+int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq, int32_t k_in, int32_t k_out,
+                   float* out_dist, int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream) {
+  if (!dist || !idx || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (P <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(NWK_ERR_ARG, "bad merge shape");
+  if (k_out > NWK_MAX_K) return fail(NWK_ERR_ARG, "k_out=%d exceeds %d", k_out, NWK_MAX_K);
+  if ((long long)k_out > (long long)P * k_in)
+    return fail(NWK_ERR_ARG, "k_out=%d exceeds the %lld candidates per query", k_out, (long long)P * k_in);
+  NWK_TRY(device_check());
+  return merge_topk(P, dist, (const long long*)idx, nq, k_in, k_out, out_dist, (long long*)out_idx, workspace,
+                    ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- running top-k state --------------------------------------------------------------
+struct nwk_topk_state {
+  long long nq;
+  int k;
+  float* pack_d;       // [2][nq][k]: slot 0 = current result, slot 1 = incoming partial
+  long long* pack_i;
+  float* tmp_d;        // [nq][k]
+  long long* tmp_i;
+  void* ws;
+  size_t ws_bytes;
+};
+
+int nwk_topk_state_create(int64_t nq, int32_t k, nwk_topk_state** out) {
+  if (!out || nq <= 0 || k <= 0 || k > NWK_MAX_K) return fail(NWK_ERR_ARG, "bad topk state shape");
+  NWK_TRY(device_check());
+  nwk_topk_state* st = new nwk_topk_state();
+  st->nq = nq;
+  st->k = k;
+  const size_t n = (size_t)nq * k;
+  st->ws_bytes = merge_workspace_bytes(2, nq, k, k);
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&st->pack_d, 2 * n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&st->pack_i, 2 * n * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMalloc(&st->tmp_d, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&st->tmp_i, n * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMalloc(&st->ws, st->ws_bytes);
+  if (e != cudaSuccess) {
+    nwk_topk_state_destroy(st);
+    return fail(NWK_ERR_CUDA, "topk state allocation failed: %s", cudaGetErrorString(e));
+  }
+  state_init_kernel<<<256, 256>>>(st->pack_d, st->pack_i, (long long)n);
+  NWK_LAUNCH_CHECK();
+  NWK_CUDA(cudaDeviceSynchronize());
+  *out = st;
+  return NWK_OK;
+}
+
+int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* idx, void* stream) {
+  if (!st || !dist || !idx) return fail(NWK_ERR_ARG, "null pointer argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)st->nq * st->k;
+  NWK_CUDA(cudaMemcpyAsync(st->pack_d + n, dist, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_i + n, idx, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  NWK_TRY(merge_topk(2, st->pack_d, st->pack_i, st->nq, st->k, st->k, st->tmp_d, st->tmp_i, st->ws, st->ws_bytes, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  return NWK_OK;
+}
+
+int nwk_topk_state_finalize(nwk_topk_state* st, float* out_dist, int64_t* out_idx, void* stream) {
+  if (!st || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)st->nq * st->k;
+  NWK_CUDA(cudaMemcpyAsync(out_dist, st->pack_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  NWK_CUDA(cudaMemcpyAsync(out_idx, st->pack_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  return NWK_OK;
+}
+
+int nwk_topk_state_destroy(nwk_topk_state* st) {
+  if (!st) return NWK_OK;
+  cudaFree(st->pack_d);
+  cudaFree(st->pack_i);
+  cudaFree(st->tmp_d);
+  cudaFree(st->tmp_i);
+  cudaFree(st->ws);
+  delete st;
+  return NWK_OK;
+}
+
+// ---- host-buffer path -----------------------------------------------------------------
+
+int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host, int64_t nq, int32_t d,
+                     int32_t k, int32_t metric, int64_t id_offset, int64_t slab_rows, float* out_dist_host,
+                     int64_t* out_idx_host, uint32_t flags, nwk_knn_stats* stats) {
+  if (!base_host || !query_host || !out_dist_host || !out_idx_host) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (nb <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > NWK_MAX_K || k > nb) return fail(NWK_ERR_ARG, "bad shape");
+  NWK_TRY(device_check());
+  std::lock_guard<std::mutex> lock(g_host.mu);
+  HostCtx& c = g_host;
+  if (!c.init) {
+    NWK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    NWK_CUDA(cudaStreamCreateWithFlags(&c.comp_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      NWK_CUDA(cudaEventCreateWithFlags(&c.copied[i], cudaEventDisableTiming));
+      NWK_CUDA(cudaEventCreateWithFlags(&c.freed[i], cudaEventDisableTiming));
+    }
+    c.init = true;
+  }
+  if (slab_rows <= 0) {
+    // >= 8 slabs so the first copy is a small part of the run, but slabs of at least 64K
+    // rows so the per-slab fixed cost stays negligible
+    slab_rows = (nb + 7) / 8;
+    if (slab_rows < 65536) slab_rows = 65536;
+    const long long max_rows = (long long)((6ull << 30) / ((size_t)d * 4));
+    if (slab_rows > max_rows) slab_rows = max_rows;
+  }
+  if (slab_rows > nb) slab_rows = nb;
+  if (slab_rows < k) slab_rows = k;
+  long long nslab = (nb + slab_rows - 1) / slab_rows;
+  // the last slab must still hold k rows (the reference asserts the same of its last
+  // batch, cu_knn.py:177): fold a short tail into the previous slab
+  if (nslab > 1 && nb - (nslab - 1) * slab_rows < k) {
+    nslab -= 1;
+    slab_rows = (nb + nslab - 1) / nslab;
+  }
+  const size_t n_out = (size_t)nq * k;
+  size_t ws_need = 0;
+  for (long long i = 0; i < nslab; ++i) {
+    long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
+    size_t w = nwk_knn_workspace_bytes(rows, nq, d, k, metric, flags);
+    if (w > ws_need) ws_need = w;
+  }
+  size_t sb = c.slab_bytes;
+  NWK_TRY(grow(&c.slab[0], &sb, (size_t)slab_rows * d * 4));
+  sb = c.slab_bytes;
+  NWK_TRY(grow(&c.slab[1], &sb, (size_t)slab_rows * d * 4));
+  c.slab_bytes = sb;
+  NWK_TRY(grow(&c.query, &c.query_bytes, (size_t)nq * d * 4));
+  NWK_TRY(grow(reinterpret_cast<char**>(&c.ws), &c.ws_bytes, ws_need));
+  if (c.part_n < n_out) {
+    if (c.part_d) cudaFree(c.part_d);
+    if (c.part_i) cudaFree(c.part_i);
+    c.part_d = nullptr; c.part_i = nullptr; c.part_n = 0;
+    NWK_CUDA(cudaMalloc(&c.part_d, n_out * sizeof(float)));
+    NWK_CUDA(cudaMalloc(&c.part_i, n_out * sizeof(long long)));
+    c.part_n = n_out;
+  }
+  nwk_topk_state* st = nullptr;
+  if (nslab > 1) NWK_TRY(nwk_topk_state_create(nq, k, &st));
+
+  nwk_knn_stats total{};
+  int rc = NWK_OK;
+  auto enqueue_copy = [&](long long i) -> int {
+    const int b = (int)(i & 1);
+    long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
+    NWK_CUDA(cudaStreamWaitEvent(c.copy_stream, c.freed[b], 0));
+    NWK_CUDA(cudaMemcpyAsync(c.slab[b], base_host + (size_t)i * slab_rows * d, (size_t)rows * d * 4,
+                             cudaMemcpyHostToDevice, c.copy_stream));
+    NWK_CUDA(cudaEventRecord(c.copied[b], c.copy_stream));
+    return NWK_OK;
+  };
+  do {
+    if ((rc = [&]() -> int {
+          NWK_CUDA(cudaMemcpyAsync(c.query, query_host, (size_t)nq * d * 4, cudaMemcpyHostToDevice, c.comp_stream));
+          // both ring slots start free
+          NWK_CUDA(cudaEventRecord(c.freed[0], c.comp_stream));
+          NWK_CUDA(cudaEventRecord(c.freed[1], c.comp_stream));
+          return NWK_OK;
+        }()) != NWK_OK) break;
+    if ((rc = enqueue_copy(0)) != NWK_OK) break;
+    for (long long i = 0; i < nslab && rc == NWK_OK; ++i) {
+      const int b = (int)(i & 1);
+      long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
+      if (i + 1 < nslab && (rc = enqueue_copy(i + 1)) != NWK_OK) break;   // overlaps with this slab's search
+      rc = [&]() -> int {
+        NWK_CUDA(cudaStreamWaitEvent(c.comp_stream, c.copied[b], 0));
+        nwk_knn_stats s1{};
+        NWK_TRY(nwk_knn_f32(c.slab[b], rows, c.query, nq, d, k, metric, id_offset + i * slab_rows, c.part_d,
+                            (int64_t*)c.part_i, c.ws, c.ws_bytes, flags, &s1, c.comp_stream));
+        NWK_CUDA(cudaEventRecord(c.freed[b], c.comp_stream));
+        total.path = s1.path;
+        total.n_fallback_queries += s1.n_fallback_queries;
+        total.total_candidates += s1.total_candidates;
+        total.total_rerank += s1.total_rerank;
+        total.gpu_launches += s1.gpu_launches;
+        if (s1.max_candidates > total.max_candidates) total.max_candidates = s1.max_candidates;
+        if (s1.max_rerank > total.max_rerank) total.max_rerank = s1.max_rerank;
+        if (st) NWK_TRY(nwk_topk_state_update(st, c.part_d, (const int64_t*)c.part_i, c.comp_stream));
+        return NWK_OK;
+      }();
+    }
+    if (rc != NWK_OK) break;
+    rc = [&]() -> int {
+      const float* fd = st ? st->pack_d : c.part_d;
+      const long long* fi = st ? st->pack_i : c.part_i;
+      NWK_CUDA(cudaMemcpyAsync(out_dist_host, fd, n_out * sizeof(float), cudaMemcpyDeviceToHost, c.comp_stream));
+      NWK_CUDA(cudaMemcpyAsync(out_idx_host, fi, n_out * sizeof(long long), cudaMemcpyDeviceToHost, c.comp_stream));
+      NWK_CUDA(cudaStreamSynchronize(c.comp_stream));
+      return NWK_OK;
+    }();
+  } while (0);
+  if (rc != NWK_OK) {
+    cudaStreamSynchronize(c.copy_stream);
+    cudaStreamSynchronize(c.comp_stream);
+  }
+  if (st) nwk_topk_state_destroy(st);
+  if (stats && rc == NWK_OK) *stats = total;
+  return rc;
+}
+
+int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0, int32_t normalize,
+                   void* stream) {
+  if (!out || rows < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad synth arguments");
+  NWK_TRY(device_check());
+  return synth_fill(out, rows, d, seed, row0, normalize, static_cast<cudaStream_t>(stream));
+}
+
+int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int64_t b0,
+                      int64_t q0, float* out, void* stream) {
+  if (!base || !query || !out) return fail(NWK_ERR_ARG, "null pointer argument");
+  NWK_TRY(device_check());
+  return tc_debug_tile(base, nb, query, nq, d, b0, q0, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// nwk_scan.cu -- fp64 exact scan, segmented top-k and the k-way merge.
+//
+// The exact scan is the engine's ground floor: every (query, base row) distance is
+// evaluated in fp64 straight from the fp32 inputs and the k smallest are selected by
+// (distance, index).  It serves three purposes:
+//   * the fallback for queries whose tensor-core candidate set cannot be certified,
+//   * the whole path for shapes the tcgen05 kernel does not take (d % 4 != 0, tiny inputs),
+//   * the on-device verifier the large parity tests sample against.
+// It replaces the same reference call sites as nwk_knn_f32 (cu_knn.py:243-257).
+//
+// The merge kernel replaces the argsort fold of merge.py:73-104.
+#include "nwk_common.cuh"
+
+namespace nwk {
+
+constexpr int SCAN_QG = 8;        // queries per CTA of the distance kernel
+constexpr int SCAN_WARPS = 8;
+constexpr int SEG = 4096;         // elements sorted per CTA of the selection kernels
+constexpr int SEG_THREADS = 512;
+
+// ---------------------------------------------------------------------------------------
+// distance kernel: dist64[f][row] for a group of SCAN_QG selected queries
+//   HBM-bound only when few queries are selected; otherwise fp64-pipe bound.
+//   bytes per launch: nb*d*4 (base read once per query group) + F*nb*8 written.
+// ---------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(SCAN_WARPS * 32)
+scan_dist_kernel(const float* __restrict__ base, long long nb, const float* __restrict__ query,
+                 int d, const int* __restrict__ qsel, int f0, int nsel,
+                 double* __restrict__ dist64) {
+  extern __shared__ float s_q[];                       // [SCAN_QG][d]
+  __shared__ double s_qn2[SCAN_QG];
+  const int g0 = f0 + blockIdx.y * SCAN_QG;            // first selected slot of this group
+  const int ng = max(0, min(SCAN_QG, f0 + nsel - g0));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < SCAN_QG * d; i += blockDim.x) {
+    int g = i / d, c = i - g * d;
+    float v = 0.f;
+    if (g < ng) {
+      long long qrow = qsel ? qsel[g0 + g] : (long long)(g0 + g);
+      v = query[qrow * d + c];
+    }
+    s_q[i] = v;
+  }
+  __syncthreads();
+  if (METRIC == NWK_METRIC_COSINE && warp < SCAN_QG) {
+    double a = 0.0;
+    for (int c = lane; c < d; c += 32) { double v = s_q[warp * d + c]; a = fma(v, v, a); }
+    a = warp_sum(a);
+    if (lane == 0) s_qn2[warp] = a;
+  }
+  __syncthreads();
+
+  const bool vec4 = (d & 3) == 0;
+  for (long long row = (long long)blockIdx.x * SCAN_WARPS + warp; row < nb;
+       row += (long long)gridDim.x * SCAN_WARPS) {
+    double acc[SCAN_QG];
+#pragma unroll
+    for (int g = 0; g < SCAN_QG; ++g) acc[g] = 0.0;
+    double bn2 = 0.0;
+    const float* brow = base + row * d;
+    if (vec4) {
+      for (int c = lane * 4; c < d; c += 128) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+        double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
+        if (METRIC == NWK_METRIC_COSINE) {
+          bn2 = fma(b0, b0, bn2); bn2 = fma(b1, b1, bn2); bn2 = fma(b2, b2, bn2); bn2 = fma(b3, b3, bn2);
+        }
+#pragma unroll
+        for (int g = 0; g < SCAN_QG; ++g) {
+          float4 q4 = *reinterpret_cast<const float4*>(s_q + g * d + c);
+          if (METRIC == NWK_METRIC_SQEUCLIDEAN) {
+            double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1;
+            double e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
+            acc[g] = fma(e0, e0, acc[g]); acc[g] = fma(e1, e1, acc[g]);
+            acc[g] = fma(e2, e2, acc[g]); acc[g] = fma(e3, e3, acc[g]);
+          } else {
+            // operation order shared with warp_exact_distance (nwk_tc.cu): bit-identical fp64
+            acc[g] = fma((double)q4.x, b0, acc[g]); acc[g] = fma((double)q4.y, b1, acc[g]);
+            acc[g] = fma((double)q4.z, b2, acc[g]); acc[g] = fma((double)q4.w, b3, acc[g]);
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) {
+        double b0 = __ldg(brow + c);
+        if (METRIC == NWK_METRIC_COSINE) bn2 = fma(b0, b0, bn2);
+#pragma unroll
+        for (int g = 0; g < SCAN_QG; ++g) {
+          double qv = s_q[g * d + c];
+          if (METRIC == NWK_METRIC_SQEUCLIDEAN) { double e = qv - b0; acc[g] = fma(e, e, acc[g]); }
+          else acc[g] = fma(qv, b0, acc[g]);
+        }
+      }
+    }
+    if (METRIC == NWK_METRIC_COSINE) bn2 = warp_sum(bn2);
+#pragma unroll
+    for (int g = 0; g < SCAN_QG; ++g) acc[g] = warp_sum(acc[g]);
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < SCAN_QG; ++g) {
+        if (g < ng) {
+          double v = acc[g];
+          if (METRIC != NWK_METRIC_SQEUCLIDEAN) v = finish_metric(METRIC, v, s_qn2[g], bn2);
+          dist64[(long long)(g0 - f0 + g) * nb + row] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// segmented top-k: each CTA sorts one segment of up to SEG (key, id) pairs of one query
+// and emits its k smallest.  Sources:
+//   SRC_IOTA   keys double [F][n], id = position           (first round of the exact scan)
+//   SRC_PAIRS  keys double + ids int64 [F][n]              (later rounds)
+//   SRC_MERGE  keys float [P][nq][k_in] + ids int64        (first round of the merge)
+// When `final_out` is set the k results go to (out_dist fp32, out_idx int64 + id_offset) at
+// row `qsel ? qsel[f] : f`, otherwise to (out_key, out_id) [F][nseg*k].
+// ---------------------------------------------------------------------------------------
+enum { SRC_IOTA = 0, SRC_PAIRS = 1, SRC_MERGE = 2 };
+
+struct SegArgs {
+  const double* in_key;
+  const long long* in_id;
+  const float* in_f32;      // SRC_MERGE
+  long long n;              // elements per query
+  long long in_stride;      // stride between queries (elements) for SRC_IOTA / SRC_PAIRS
+  long long nq;             // SRC_MERGE: queries (partial stride = nq * k_in)
+  int k_in;                 // SRC_MERGE
+  int k;
+  double* out_key;
+  long long* out_id;
+  long long out_stride;     // nseg * k
+  float* out_dist;
+  long long* out_idx;
+  long long id_offset;
+  const int* qsel;
+  int f0;                   // slot offset into qsel for this launch
+  int final_out;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_topk_kernel(SegArgs a) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* keys = reinterpret_cast<double*>(s_raw);
+  long long* ids = reinterpret_cast<long long*>(s_raw + sizeof(double) * SEG);
+  const long long f = blockIdx.y;
+  const long long seg = blockIdx.x;
+  const long long e0 = seg * SEG;
+  const int valid = (int)min((long long)SEG, a.n - e0);
+  const int n2 = max(next_pow2(valid), 2);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+  for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+    double kv = INF;
+    long long iv = 0x7fffffffffffffffLL;
+    if (t < valid) {
+      long long e = e0 + t;
+      if (SRC == SRC_IOTA) {
+        kv = a.in_key[f * a.in_stride + e];
+        iv = e;
+      } else if (SRC == SRC_PAIRS) {
+        kv = a.in_key[f * a.in_stride + e];
+        iv = a.in_id[f * a.in_stride + e];
+      } else {
+        long long p = e / a.k_in, j = e - p * a.k_in;
+        long long off = (p * a.nq + f) * a.k_in + j;
+        kv = (double)a.in_f32[off];
+        iv = a.in_id[off];
+      }
+      if (kv != kv) kv = INF;   // NaN sorts last
+    }
+    keys[t] = kv;
+    ids[t] = iv;
+  }
+  block_bitonic_sort(keys, ids, n2);
+
+  for (int t = threadIdx.x; t < a.k; t += blockDim.x) {
+    double kv = t < n2 ? keys[t] : INF;
+    long long iv = t < n2 ? ids[t] : 0x7fffffffffffffffLL;
+    if (a.final_out) {
+      long long row = a.qsel ? (long long)a.qsel[a.f0 + f] : f;
+      a.out_dist[row * a.k + t] = (float)kv;
+      a.out_idx[row * a.k + t] = (iv == 0x7fffffffffffffffLL) ? -1 : iv + a.id_offset;
+    } else {
+      a.out_key[f * a.out_stride + seg * a.k + t] = kv;
+      a.out_id[f * a.out_stride + seg * a.k + t] = iv;
+    }
+  }
+}
+
+static int seg_smem_optin() {
+  static bool done = false;
+  if (!done) {
+    const int bytes = SEG * 16;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(seg_topk_kernel<SRC_IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "smem opt-in failed: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(seg_topk_kernel<SRC_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "smem opt-in failed: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(seg_topk_kernel<SRC_MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "smem opt-in failed: %s", cudaGetErrorString(e));
+    done = true;
+  }
+  return NWK_OK;
+}
+
+// Reduce [F][n] candidates (described by `a`, first-round source SRC) to the final k per query.
+// ping / pong: scratch of F * ceil(n/SEG) * k pairs each.
+template <int SRC>
+static int run_topk_rounds(SegArgs a, int F, double* ping_k, long long* ping_i, double* pong_k,
+                           long long* pong_i, cudaStream_t s) {
+  NWK_TRY(seg_smem_optin());
+  const int smem = SEG * 16;
+  long long n = a.n;
+  bool first = true;
+  float* out_dist = a.out_dist;
+  long long* out_idx = a.out_idx;
+  while (true) {
+    long long nseg = (n + SEG - 1) / SEG;
+    a.n = n;
+    a.final_out = (nseg == 1);
+    a.out_key = ping_k;
+    a.out_id = ping_i;
+    a.out_stride = nseg * a.k;
+    a.out_dist = out_dist;
+    a.out_idx = out_idx;
+    dim3 grid((unsigned)nseg, (unsigned)F);
+    if (first) seg_topk_kernel<SRC><<<grid, SEG_THREADS, smem, s>>>(a);
+    else seg_topk_kernel<SRC_PAIRS><<<grid, SEG_THREADS, smem, s>>>(a);
+    NWK_LAUNCH_CHECK();
+    if (nseg == 1) break;
+    // next round reads what this round wrote
+    a.in_key = ping_k;
+    a.in_id = ping_i;
+    a.in_stride = nseg * a.k;
+    n = nseg * a.k;
+    first = false;
+    double* tk = ping_k; ping_k = pong_k; pong_k = tk;
+    long long* ti = ping_i; ping_i = pong_i; pong_i = ti;
+  }
+  return NWK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact scan driver
+// ---------------------------------------------------------------------------------------
+static long long scan_chunk_queries(long long nb) {
+  const long long budget = 512ll << 20;
+  long long fc = budget / (nb * 8);
+  fc = fc / SCAN_QG * SCAN_QG;
+  if (fc < SCAN_QG) fc = SCAN_QG;
+  if (fc > 4096) fc = 4096;
+  return fc;
+}
+
+size_t exact_scan_workspace_bytes(long long nb, long long nsel, int k) {
+  long long fc = scan_chunk_queries(nb);
+  if (fc > nsel) fc = (nsel + SCAN_QG - 1) / SCAN_QG * SCAN_QG;
+  if (fc < SCAN_QG) fc = SCAN_QG;
+  long long nseg = (nb + SEG - 1) / SEG;
+  size_t bytes = 0;
+  bytes += align_up((size_t)fc * nb * 8, 256);
+  bytes += 2 * (align_up((size_t)fc * nseg * k * 8, 256) * 2);
+  return bytes + 4096;
+}
+
+// qsel: device list of query rows (nullptr = 0..nsel-1).  Results are written to row
+// qsel[i] of out_dist / out_idx.
+int exact_scan(const float* base, long long nb, const float* query, int d, int k, int metric,
+               long long id_offset, const int* qsel, long long nsel, float* out_dist,
+               long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (nsel == 0) return NWK_OK;
+  if (ws_bytes < exact_scan_workspace_bytes(nb, nsel, k))
+    return fail(NWK_ERR_WORKSPACE, "exact scan workspace too small");
+  long long fc = scan_chunk_queries(nb);
+  if (fc > nsel) fc = (nsel + SCAN_QG - 1) / SCAN_QG * SCAN_QG;
+  long long nseg = (nb + SEG - 1) / SEG;
+  Arena ar(ws, ws_bytes);
+  double* dist64 = ar.take<double>((size_t)fc * nb);
+  double* ping_k = ar.take<double>((size_t)fc * nseg * k);
+  long long* ping_i = ar.take<long long>((size_t)fc * nseg * k);
+  double* pong_k = ar.take<double>((size_t)fc * nseg * k);
+  long long* pong_i = ar.take<long long>((size_t)fc * nseg * k);
+
+  const size_t q_smem = (size_t)SCAN_QG * d * sizeof(float);
+  if (q_smem > 200 * 1024) return fail(NWK_ERR_ARG, "d=%d too large for the exact scan", d);
+  static bool optin = false;
+  if (!optin) {
+    NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    optin = true;
+  }
+  const int sms = sm_count();
+  for (long long f0 = 0; f0 < nsel; f0 += fc) {
+    const int nf = (int)min(fc, nsel - f0);
+    const int groups = (nf + SCAN_QG - 1) / SCAN_QG;
+    long long row_blocks = (nb + SCAN_WARPS - 1) / SCAN_WARPS;
+    long long want = (long long)sms * 8 / groups;       // ~8 CTAs per SM in total
+    if (want < 1) want = 1;
+    if (row_blocks > want) row_blocks = want;
+    dim3 grid((unsigned)row_blocks, (unsigned)groups);
+    switch (metric) {
+      case NWK_METRIC_SQEUCLIDEAN:
+        scan_dist_kernel<NWK_METRIC_SQEUCLIDEAN><<<grid, SCAN_WARPS * 32, q_smem, s>>>(
+            base, nb, query, d, qsel, (int)f0, nf, dist64);
+        break;
+      case NWK_METRIC_COSINE:
+        scan_dist_kernel<NWK_METRIC_COSINE><<<grid, SCAN_WARPS * 32, q_smem, s>>>(
+            base, nb, query, d, qsel, (int)f0, nf, dist64);
+        break;
+      default:
+        scan_dist_kernel<NWK_METRIC_DOT><<<grid, SCAN_WARPS * 32, q_smem, s>>>(
+            base, nb, query, d, qsel, (int)f0, nf, dist64);
+        break;
+    }
+    NWK_LAUNCH_CHECK();
+    SegArgs a{};
+    a.in_key = dist64;
+    a.n = nb;
+    a.in_stride = nb;
+    a.k = k;
+    a.out_dist = out_dist;
+    a.out_idx = out_idx;
+    a.id_offset = id_offset;
+    a.qsel = qsel;
+    a.f0 = (int)f0;
+    if (!qsel) {
+      // identity selection: rows f0 .. f0+nf-1
+      a.out_dist = out_dist + f0 * k;
+      a.out_idx = out_idx + f0 * k;
+    }
+    NWK_TRY(run_topk_rounds<SRC_IOTA>(a, nf, ping_k, ping_i, pong_k, pong_i, s));
+  }
+  return NWK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// merge driver
+// ---------------------------------------------------------------------------------------
+size_t merge_workspace_bytes(int P, long long nq, int k_in, int k_out) {
+  long long n = (long long)P * k_in;
+  long long nseg = (n + SEG - 1) / SEG;
+  if (nseg <= 1) return 256;
+  return 2 * (align_up((size_t)nq * nseg * k_out * 8, 256) * 2) + 4096;
+}
+
+int merge_topk(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
+               float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (nq == 0) return NWK_OK;
+  if (ws_bytes < merge_workspace_bytes(P, nq, k_in, k_out))
+    return fail(NWK_ERR_WORKSPACE, "merge workspace too small");
+  long long n = (long long)P * k_in;
+  long long nseg = (n + SEG - 1) / SEG;
+  Arena ar(ws, ws_bytes);
+  double* ping_k = nullptr; long long* ping_i = nullptr;
+  double* pong_k = nullptr; long long* pong_i = nullptr;
+  if (nseg > 1) {
+    ping_k = ar.take<double>((size_t)nq * nseg * k_out);
+    ping_i = ar.take<long long>((size_t)nq * nseg * k_out);
+    pong_k = ar.take<double>((size_t)nq * nseg * k_out);
+    pong_i = ar.take<long long>((size_t)nq * nseg * k_out);
+  }
+  // grid.y is limited to 65535: walk the queries in slices
+  const long long SLICE = 32768;
+  for (long long q0 = 0; q0 < nq; q0 += SLICE) {
+    long long nf = min(SLICE, nq - q0);
+    SegArgs a{};
+    a.in_f32 = dist + q0 * k_in;
+    a.in_id = idx + q0 * k_in;
+    a.n = n;
+    a.nq = nq;
+    a.k_in = k_in;
+    a.k = k_out;
+    a.out_dist = out_dist + q0 * k_out;
+    a.out_idx = out_idx + q0 * k_out;
+    a.id_offset = 0;
+    NWK_TRY(run_topk_rounds<SRC_MERGE>(a, (int)nf, ping_k, ping_i, pong_k, pong_i, s));
+  }
+  return NWK_OK;
+}
+
+}  // namespace nwk

@@ -1,0 +1,747 @@
+// nwk_tc.cu -- tensor-core candidate stage + fp64 finish for exact brute-force kNN.
+//
+// Pipeline of one nwk_knn_f32 call (replaces knn() at cu_knn.py:243-257 of the reference):
+//
+//   rownorm_kernel   per base row j: alpha_j, beta_j so that key(q,j) = alpha_j + beta_j*(q.b_j)
+//                    orders rows like the requested distance (|b|^2 - 2 q.b, -q.b/|b|, -q.b);
+//                    also max |b|.                                     HBM-bound, B*d*4 bytes.
+//   tc_kernel<SAMPLE>  TF32 tcgen05 GEMM of every query tile against a strided sample of base
+//                    tiles; epilogue keeps the m smallest keys per query -> threshold tau_q
+//                    such that about `target` rows of the whole base fall below it.
+//   tc_kernel<FILTER>  the same GEMM over the whole base; the epilogue compares each key with
+//                    tau_q straight out of TMEM and appends the (rare) survivors to a
+//                    per-query candidate log.  The distance matrix never reaches HBM.
+//                    Tensor-pipe bound: 2*Q*B*d FLOP.
+//   finish_kernel    per query: sort the log, take every candidate whose TF32 key lies within
+//                    2*eps of the k-th (eps = proven TF32 error bound), recompute those in
+//                    fp64 from the fp32 inputs, order by (distance, index), emit k.
+//                    A query is *certified* when tau_q lies above that band (so no row outside
+//                    the log can belong to the true top-k); the others go to the fp64 scan.
+//
+// Tile shape: 128 queries (MMA M, one TMEM lane per query) x 256 base rows (MMA N), K-blocks
+// of 32 fp32 = one 128-byte swizzle span, 4-stage TMA ring (48 KB per stage), two TMEM
+// accumulator stages of 256 columns so the epilogue of pair p overlaps the MMAs of pair p+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "nwk_common.cuh"
+#include "nwk_ptx.cuh"
+
+namespace nwk {
+
+int exact_scan(const float* base, long long nb, const float* query, int d, int k, int metric,
+               long long id_offset, const int* qsel, long long nsel, float* out_dist,
+               long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t exact_scan_workspace_bytes(long long nb, long long nsel, int k);
+
+constexpr int TQ = 128;
+constexpr int TB = 256;
+constexpr int BK = 32;
+constexpr int UMMA_K = 8;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TC_THREADS = 256;
+constexpr int STAGE_A_BYTES = TQ * BK * 4;     // 16 KB
+constexpr int STAGE_B_BYTES = TB * BK * 4;     // 32 KB
+constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int M_MAX = 32;                      // longest per-query sample list
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + M_MAX * TQ * 4 + 256 + 1024;
+constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
+constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
+constexpr int TC_MAX_K = 256;
+constexpr int FIN_THREADS = 256;
+
+enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
+enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
+
+struct TcParams {
+  int d, nKB;
+  long long nq, nb;
+  int nQT, nT;
+  int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
+  int nS, m;                // SAMPLE: sample tiles, list length
+  const float* alpha;       // [nT*TB]
+  const float* beta;        // [nT*TB]
+  float* tau;               // [nQT*TQ]
+  unsigned int* cnt;        // [nq]
+  unsigned long long* log;  // [nq][LOG_CAP]
+  float* dump;              // MODE_DUMP: [TQ][TB]
+  int dump_qt, dump_t;
+  int* err;
+};
+
+// ---------------------------------------------------------------------------------------
+// rownorm: alpha / beta per base row (padded to whole tiles) + max norm
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rownorm_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int metric,
+               float* __restrict__ alpha, float* __restrict__ beta, unsigned int* __restrict__ bn2max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
+  float local_max = 0.f;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
+    if (row >= nb) {
+      if (lane == 0) { alpha[row] = INF; beta[row] = 0.f; }
+      continue;
+    }
+    const float* brow = base + row * d;
+    double a = 0.0;
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(brow + c));
+      a = fma((double)v.x, (double)v.x, a);
+      a = fma((double)v.y, (double)v.y, a);
+      a = fma((double)v.z, (double)v.z, a);
+      a = fma((double)v.w, (double)v.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) {
+      float al = 0.f, be = -1.f;
+      if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f; }
+      else if (metric == NWK_METRIC_COSINE) {
+        if (a > 0.0) be = (float)(-1.0 / sqrt(a)); else { al = INF; be = 0.f; }
+      }
+      alpha[row] = al;
+      beta[row] = be;
+      local_max = fmaxf(local_max, __double2float_ru(a));
+    }
+  }
+  if (lane == 0 && local_max > 0.f) atomicMax(bn2max, __float_as_uint(local_max));
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// schedule shared by the three roles of tc_kernel: the sequence of (query tile, base tile)
+// pairs this CTA walks, in an order that keeps concurrently running CTAs on the same base
+// chunk (so a base tile is fetched from HBM once and served from L2 to the other CTAs).
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+struct Sched {
+  int nUnits, nQT, nT, G, nS, dump_qt, dump_t;
+  int u, i, len, qt, c;
+  __device__ explicit Sched(const TcParams& p)
+      : nUnits(p.nUnits), nQT(p.nQT), nT(p.nT), G(p.G), nS(p.nS), dump_qt(p.dump_qt), dump_t(p.dump_t),
+        u((int)blockIdx.x - (int)gridDim.x), i(0), len(0), qt(0), c(0) {}
+  // advance to the next pair; returns false when the CTA is done
+  __device__ __forceinline__ bool next(int& out_qt, int& out_t, bool& first, bool& last) {
+    if (i >= len) {
+      u += gridDim.x;
+      if (MODE == MODE_FILTER) {
+        if (u >= nUnits) return false;
+        c = u / nQT;
+        qt = u - c * nQT;
+        len = min(G, nT - c * G);
+      } else if (MODE == MODE_SAMPLE) {
+        if (u >= nQT) return false;
+        qt = u;
+        len = nS;
+      } else {
+        if (u >= 1) return false;
+        qt = dump_qt;
+        len = 1;
+      }
+      i = 0;
+    }
+    out_qt = qt;
+    if (MODE == MODE_FILTER) out_t = c * G + i;
+    else if (MODE == MODE_SAMPLE) out_t = (int)(((long long)i * nT) / nS);
+    else out_t = dump_t;
+    first = (i == 0);
+    last = (i == len - 1);
+    ++i;
+    return true;
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
+          const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled operand tiles
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_list = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);           // [M_MAX][TQ]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + M_MAX * TQ * 4);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(s_tmem, ACC_STAGES * TB);      // 512 columns
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      Sched<MODE> sch(p);
+      int qt, t; bool first, last;
+      int stage = 0; uint32_t phase = 0;
+      bool ok = true;
+      while (ok && sch.next(qt, t, first, last)) {
+        for (int kb = 0; kb < p.nKB; ++kb) {
+          if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
+          unsigned char* sa = smem + stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * BK, qt * TQ);
+          ptx::tma_load_2d(sa + STAGE_A_BYTES, &tmap_b, &full_bar[stage], kb * BK, t * TB);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      Sched<MODE> sch(p);
+      int qt, t; bool first, last;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = ptx::umma_idesc_tf32(TQ, TB);
+      bool ok = true;
+      while (ok && sch.next(qt, t, first, last)) {
+        if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TB;
+        for (int kb = 0; kb < p.nKB; ++kb) {
+          if (!ptx::mbar_wait(&full_bar[stage], phase, p.err, ERR_MMA_FULL)) { ok = false; break; }
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = ptx::umma_desc_sw128(sa);
+          const uint64_t db = ptx::umma_desc_sw128(sa + STAGE_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 8 fp32 = 32 B inside the 128 B swizzle span: +2 in 16-byte units
+            ptx::mma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        ptx::tc_commit(&tfull_bar[acc]);            // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 128 threads, thread <-> TMEM lane <-> query row of the tile =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    Sched<MODE> sch(p);
+    int qt, t; bool first, last;
+    int acc = 0; uint32_t acc_phase = 0;
+    const float INF = __int_as_float(0x7f800000);
+    float tau = -INF;
+    long long q = 0;
+    int filled = 0;   // SAMPLE: how many list slots hold real values
+    bool ok = true;
+    while (ok && sch.next(qt, t, first, last)) {
+      if (first) {
+        q = (long long)qt * TQ + row_in_tile;
+        if (MODE == MODE_FILTER) {
+          tau = (q < p.nq) ? p.tau[q] : -INF;
+        } else if (MODE == MODE_SAMPLE) {
+          tau = (q < p.nq) ? INF : -INF;
+          filled = 0;
+          for (int j = 0; j < p.m; ++j) s_list[j * TQ + row_in_tile] = INF;
+        }
+      }
+      if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
+      const float4* al4 = reinterpret_cast<const float4*>(p.alpha + (long long)t * TB);
+      const float4* be4 = reinterpret_cast<const float4*>(p.beta + (long long)t * TB);
+      const long long row0 = (long long)t * TB;
+
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32(taddr, va);
+#pragma unroll
+      for (int ch = 0; ch < TB / 32; ++ch) {
+        ptx::tmem_wait_ld();
+        uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+        if (ch + 1 < TB / 32) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
+        if (MODE == MODE_DUMP) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            p.dump[(long long)row_in_tile * TB + ch * 32 + j] = __uint_as_float(cur[j]);
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 al = __ldg(al4 + ch * 8 + j4);
+            const float4 be = __ldg(be4 + ch * 8 + j4);
+            float k0 = fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x);
+            float k1 = fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y);
+            float k2 = fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z);
+            float k3 = fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w);
+            if ((k0 < tau) | (k1 < tau) | (k2 < tau) | (k3 < tau)) {
+              float kk[4] = {k0, k1, k2, k3};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float key = kk[e];
+                if (key < tau) {
+                  if (MODE == MODE_FILTER) {
+                    const unsigned int slot = atomicAdd(p.cnt + q, 1u);
+                    if (slot < LOG_CAP) {
+                      const unsigned long long rec =
+                          (static_cast<unsigned long long>(f2ord(key)) << 32) |
+                          static_cast<unsigned long long>(row0 + ch * 32 + j4 * 4 + e);
+                      p.log[q * LOG_CAP + slot] = rec;
+                    }
+                  } else {
+                    // insertion into the ascending list of the m smallest keys seen
+                    int pos = min(filled, p.m - 1);
+                    while (pos > 0 && s_list[(pos - 1) * TQ + row_in_tile] > key) {
+                      s_list[pos * TQ + row_in_tile] = s_list[(pos - 1) * TQ + row_in_tile];
+                      --pos;
+                    }
+                    s_list[pos * TQ + row_in_tile] = key;
+                    if (filled < p.m) ++filled;
+                    if (filled == p.m) tau = s_list[(p.m - 1) * TQ + row_in_tile];
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      if (MODE == MODE_SAMPLE && last && q < p.nq) p.tau[q] = (filled == p.m) ? tau : INF;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, ACC_STAGES * TB);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finish: select within the proven error band, re-rank in fp64, emit top-k, certify
+// ---------------------------------------------------------------------------------------
+struct FinParams {
+  const float* base; const float* query;
+  long long nb, nq; int d, k, metric;
+  long long id_offset;
+  const float* tau; const unsigned int* cnt; const unsigned long long* log;
+  const unsigned int* bn2max;
+  float c_err;                 // TF32 dot-product relative error constant
+  float* out_dist; long long* out_idx;
+  int* fail_cnt; int* fail_list;
+  unsigned long long* stat_sum; // [0] sum cnt, [1] sum rerank
+  unsigned int* stat_max;       // [0] max cnt, [1] max rerank
+};
+
+// fp64 distance of one base row to the query held in shared memory, computed by one warp.
+// Same operation order as scan_dist_kernel so both exact paths agree bit for bit.
+__device__ __forceinline__ double warp_exact_distance(int metric, const float* s_q, const float* brow,
+                                                      int d, double qn2, int lane) {
+  double acc = 0.0, bn2 = 0.0;
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+    float4 q4 = *reinterpret_cast<const float4*>(s_q + c);
+    double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
+    if (metric == NWK_METRIC_COSINE) {
+      bn2 = fma(b0, b0, bn2); bn2 = fma(b1, b1, bn2); bn2 = fma(b2, b2, bn2); bn2 = fma(b3, b3, bn2);
+    }
+    if (metric == NWK_METRIC_SQEUCLIDEAN) {
+      double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
+      acc = fma(e0, e0, acc); acc = fma(e1, e1, acc); acc = fma(e2, e2, acc); acc = fma(e3, e3, acc);
+    } else {
+      acc = fma((double)q4.x, b0, acc); acc = fma((double)q4.y, b1, acc);
+      acc = fma((double)q4.z, b2, acc); acc = fma((double)q4.w, b3, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (metric == NWK_METRIC_SQEUCLIDEAN) return acc;
+  if (metric == NWK_METRIC_COSINE) bn2 = warp_sum(bn2);
+  return finish_metric(metric, acc, qn2, bn2);
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finish_kernel(const FinParams p) {
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(fin_smem);            // [LOG_CAP]
+  double* s_key = reinterpret_cast<double*>(fin_smem + LOG_CAP * 8);                      // [RERANK_MAX]
+  long long* s_id = reinterpret_cast<long long*>(fin_smem + LOG_CAP * 8 + RERANK_MAX * 8);
+  float* s_q = reinterpret_cast<float*>(fin_smem + LOG_CAP * 8 + RERANK_MAX * 16);        // [d]
+  __shared__ double s_red[FIN_THREADS / 32];
+  __shared__ int s_R;
+  __shared__ int s_fail;
+
+  const long long q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int total = p.cnt[q];
+  const int c = (int)min(total, (unsigned int)LOG_CAP);
+  const int n2 = max(next_pow2(c), 2);
+
+  for (int i = threadIdx.x; i < n2; i += blockDim.x)
+    s_log[i] = (i < c) ? p.log[q * LOG_CAP + i] : ~0ull;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.query[q * p.d + i];
+  block_bitonic_sort_u64(s_log, n2);      // (contains the __syncthreads the loads above need)
+  if (warp == 0) {
+    // |q|^2 in the same operation order as scan_dist_kernel
+    double a = 0.0;
+    for (int c2 = lane; c2 < p.d; c2 += 32) { double v = s_q[c2]; a = fma(v, v, a); }
+    a = warp_sum(a);
+    if (lane == 0) s_red[0] = a;
+  }
+  __syncthreads();
+  const double qn2 = s_red[0];
+
+  if (threadIdx.x == 0) {
+    int fail = 0, R = 0;
+    if (total > (unsigned int)LOG_CAP || c < p.k) {
+      fail = 1;
+    } else {
+      // proven bound on |tf32 key - exact key| for this query (see DESIGN.md "error bound")
+      const double qn = sqrt(qn2);
+      const double bnmax = sqrt((double)__uint_as_float(*p.bn2max));
+      double eps = (double)p.c_err * qn;
+      if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps *= 2.0 * bnmax;
+      else if (p.metric == NWK_METRIC_DOT) eps *= bnmax;
+      const float key_k = ord2f((uint32_t)(s_log[p.k - 1] >> 32));
+      // inflate by the fp32 rounding of alpha + beta*acc itself
+      const float thr = __double2float_ru((double)key_k + 2.0 * eps * 1.0001 +
+                                          4.0e-7 * fabs((double)key_k) + 1e-30);
+      const float tau = p.tau[q];
+      if (!(thr < tau)) fail = 1;          // band reaches the logging threshold: cannot certify
+      // R = number of logged keys <= thr (log is sorted)
+      const uint32_t thr_ord = f2ord(thr);
+      int lo = p.k, hi = c;                // first index in [k, c) with key > thr
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((uint32_t)(s_log[mid] >> 32) <= thr_ord) lo = mid + 1; else hi = mid;
+      }
+      R = lo;
+      if (R > RERANK_MAX) { fail = 1; R = RERANK_MAX; }
+    }
+    s_fail = fail;
+    s_R = R;
+    atomicAdd(p.stat_sum + 0, (unsigned long long)total);
+    atomicAdd(p.stat_sum + 1, (unsigned long long)R);
+    atomicMax(p.stat_max + 0, total);
+    atomicMax(p.stat_max + 1, (unsigned int)R);
+    if (fail) {
+      int slot = atomicAdd(p.fail_cnt, 1);
+      p.fail_list[slot] = (int)q;
+    }
+  }
+  __syncthreads();
+  if (s_fail) return;
+  const int R = s_R;
+  const int r2 = max(next_pow2(R), 2);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+  for (int i = warp; i < r2; i += FIN_THREADS / 32) {
+    if (i < R) {
+      const long long row = (long long)(s_log[i] & 0xffffffffull);
+      double dist = warp_exact_distance(p.metric, s_q, p.base + row * p.d, p.d, qn2, lane);
+      if (lane == 0) { s_key[i] = (dist != dist) ? INF : dist; s_id[i] = row; }
+    } else if (lane == 0) {
+      s_key[i] = INF;
+      s_id[i] = 0x7fffffffffffffffLL;
+    }
+  }
+  block_bitonic_sort(s_key, s_id, r2);
+  for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+    p.out_dist[q * p.k + j] = (float)s_key[j];
+    p.out_idx[q * p.k + j] = s_id[j] + p.id_offset;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym)
+      return fail(NWK_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  *out = fn;
+  return NWK_OK;
+}
+
+static int make_tmap(CUtensorMap* tm, const float* ptr, long long rows, int d, int box_rows) {
+  EncodeTiledFn enc;
+  NWK_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NWK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NWK_OK;
+}
+
+static int tc_optin() {
+  static bool done = false;
+  if (!done) {
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    done = true;
+  }
+  return NWK_OK;
+}
+
+bool tc_path_supported(long long nb, long long nq, int d, int k) {
+  return (d % 4 == 0) && d >= 4 && k <= TC_MAX_K && nb >= 1 && nq >= 1 &&
+         nb < (1ll << 31) && nq < (1ll << 31) && (long long)d * 4 < (1ll << 31);
+}
+
+struct TcPlan {
+  int nQT, nT, nKB, G, nChunks, nUnits, nS, m, target;
+  bool sample;
+  long long nb_pad, nq_pad;
+};
+
+static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms) {
+  TcPlan pl{};
+  pl.nQT = (int)((nq + TQ - 1) / TQ);
+  pl.nT = (int)((nb + TB - 1) / TB);
+  pl.nKB = (d + BK - 1) / BK;
+  pl.nb_pad = (long long)pl.nT * TB;
+  pl.nq_pad = (long long)pl.nQT * TQ;
+  long long pairs = (long long)pl.nQT * pl.nT;
+  long long g = pairs / ((long long)sms * 8);
+  pl.G = (int)(g < 1 ? 1 : (g > 16 ? 16 : g));
+  pl.nChunks = (pl.nT + pl.G - 1) / pl.G;
+  pl.nUnits = pl.nChunks * pl.nQT;
+  pl.target = 3 * k + 256;
+  if (pl.target < 768) pl.target = 768;
+  // sampling only pays when the base is much larger than the population we aim to log
+  pl.sample = nb > 2ll * pl.target;
+  if (pl.sample) {
+    long long want_rows = (24ll * nb + pl.target - 1) / pl.target;   // aims at m ~ 24
+    long long ns = (want_rows + TB - 1) / TB;
+    if (ns < 1) ns = 1;
+    if (ns > pl.nT) ns = pl.nT;
+    pl.nS = (int)ns;
+    // rows actually covered by the sample tiles (the last base tile may be partial)
+    long long rows = 0;
+    for (int i = 0; i < pl.nS; ++i) {
+      long long t = ((long long)i * pl.nT) / pl.nS;
+      long long r = nb - t * TB;
+      rows += r < TB ? r : TB;
+    }
+    double mm = (double)pl.target * (double)rows / (double)nb;
+    int m = (int)(mm + 0.5);
+    if (m < 4) m = 4;
+    if (m > M_MAX) m = M_MAX;
+    pl.m = m;
+  }
+  return pl;
+}
+
+size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
+  TcPlan pl = make_plan(nb, nq, d, k, 148);
+  size_t bytes = 0;
+  bytes += align_up((size_t)pl.nb_pad * 4, 256) * 2;        // alpha, beta
+  bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
+  bytes += align_up((size_t)nq * 4, 256);                   // cnt
+  bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
+  bytes += align_up((size_t)nq * 4, 256);                   // fail list
+  bytes += 4096;                                            // scalars
+  // fallback scan for up to 64 queries is always provisioned; more is handled in rounds
+  bytes += exact_scan_workspace_bytes(nb, 64, k) + 256;
+  return bytes + 4096;
+}
+
+struct Scalars {            // one 256-byte block of device scalars, zeroed per call
+  unsigned int bn2max;
+  int err;
+  int fail_cnt;
+  unsigned int stat_max[2];
+  unsigned int pad;
+  unsigned long long stat_sum[2];
+};
+
+int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
+           long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
+           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s) {
+  NWK_TRY(tc_optin());
+  const int sms = sm_count();
+  TcPlan pl = make_plan(nb, nq, d, k, sms);
+  Arena ar(ws, ws_bytes);
+  float* alpha = ar.take<float>((size_t)pl.nb_pad);
+  float* beta = ar.take<float>((size_t)pl.nb_pad);
+  float* tau = ar.take<float>((size_t)pl.nq_pad);
+  unsigned int* cnt = ar.take<unsigned int>((size_t)nq);
+  unsigned long long* log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
+  int* fail_list = ar.take<int>((size_t)nq);
+  Scalars* sc = ar.take<Scalars>(1);
+  ar.off = align_up(ar.off, 256);
+  void* scan_ws = ar.base + ar.off;
+  if (ar.off > ws_bytes) return fail(NWK_ERR_WORKSPACE, "workspace too small for the tensor-core path");
+  size_t scan_ws_bytes = ws_bytes - ar.off;
+
+  const long long launches0 = g_launches.load();
+  const bool profile = stats && (flags & NWK_FLAG_PROFILE);
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (profile) {
+    for (int i = 0; i < 6; ++i) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[0], s);
+  }
+  NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
+  NWK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, s));
+
+  {
+    long long blocks = (pl.nb_pad + 7) / 8;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    rownorm_kernel<<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, metric, alpha, beta, &sc->bn2max);
+    NWK_LAUNCH_CHECK();
+  }
+
+  if (profile) cudaEventRecord(ev[1], s);
+  CUtensorMap tm_q, tm_b;
+  NWK_TRY(make_tmap(&tm_q, query, nq, d, TQ));
+  NWK_TRY(make_tmap(&tm_b, base, nb, d, TB));
+
+  TcParams p{};
+  p.d = d; p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
+  p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.m = pl.m;
+  p.alpha = alpha; p.beta = beta; p.tau = tau; p.cnt = cnt; p.log = log; p.err = &sc->err;
+
+
+  if (pl.sample) {
+    int grid = pl.nQT < sms ? pl.nQT : sms;
+    tc_kernel<MODE_SAMPLE><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    NWK_LAUNCH_CHECK();
+  } else {
+    fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
+    NWK_LAUNCH_CHECK();
+  }
+  if (profile) cudaEventRecord(ev[2], s);
+  {
+    int grid = pl.nUnits < sms ? pl.nUnits : sms;
+    tc_kernel<MODE_FILTER><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    NWK_LAUNCH_CHECK();
+  }
+  if (profile) cudaEventRecord(ev[3], s);
+
+  FinParams f{};
+  f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
+  f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.bn2max = &sc->bn2max;
+  // TF32 operands carry 11 significant bits (truncation error < 2^-10 each, product < 2^-9),
+  // accumulation over d terms in fp32 adds at most d * 2^-22 relative to sum |q_i b_i|.
+  f.c_err = (float)(1.0 / 512.0 * 1.001 + (double)d / 4194304.0);
+  f.out_dist = out_dist; f.out_idx = out_idx; f.fail_cnt = &sc->fail_cnt; f.fail_list = fail_list;
+  f.stat_sum = sc->stat_sum; f.stat_max = sc->stat_max;
+  {
+    const int fin_smem = LOG_CAP * 8 + RERANK_MAX * 16 + d * 4 + 16;
+    static int fin_optin = 0;
+    if (fin_smem > fin_optin) {
+      NWK_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem));
+      fin_optin = fin_smem;
+    }
+    finish_kernel<<<(unsigned)nq, FIN_THREADS, fin_smem, s>>>(f);
+    NWK_LAUNCH_CHECK();
+  }
+  if (profile) cudaEventRecord(ev[4], s);
+
+  Scalars h{};
+  NWK_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+  NWK_CUDA(cudaStreamSynchronize(s));
+  if (h.err != 0) return fail(NWK_ERR_INTERNAL, "tcgen05 pipeline watchdog expired (role code %d)", h.err);
+
+  if (h.fail_cnt > 0 && !(flags & NWK_FLAG_NO_FALLBACK)) {
+    // uncertified queries: fp64 scan, in rounds that fit the provisioned scratch
+    long long done = 0;
+    while (done < h.fail_cnt) {
+      long long n = h.fail_cnt - done;
+      while (n > 8 && exact_scan_workspace_bytes(nb, n, k) > scan_ws_bytes) n = (n + 1) / 2;
+      if (exact_scan_workspace_bytes(nb, n, k) > scan_ws_bytes)
+        return fail(NWK_ERR_WORKSPACE, "workspace too small for the exact fallback");
+      NWK_TRY(exact_scan(base, nb, query, d, k, metric, id_offset, fail_list + done, n, out_dist, out_idx,
+                         scan_ws, scan_ws_bytes, s));
+      done += n;
+    }
+  }
+  if (profile) cudaEventRecord(ev[5], s);
+  NWK_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->path = 1;
+    stats->n_fallback_queries = h.fail_cnt;
+    stats->max_candidates = (int)h.stat_max[0];
+    stats->max_rerank = (int)h.stat_max[1];
+    stats->total_candidates = (long long)h.stat_sum[0];
+    stats->total_rerank = (long long)h.stat_sum[1];
+    stats->gpu_launches = (int)(g_launches.load() - launches0);
+    if (profile) {
+      cudaEventElapsedTime(&stats->ms_rownorm, ev[0], ev[1]);
+      cudaEventElapsedTime(&stats->ms_sample, ev[1], ev[2]);
+      cudaEventElapsedTime(&stats->ms_filter, ev[2], ev[3]);
+      cudaEventElapsedTime(&stats->ms_finish, ev[3], ev[4]);
+      cudaEventElapsedTime(&stats->ms_fallback, ev[4], ev[5]);
+      cudaEventElapsedTime(&stats->ms_total, ev[0], ev[5]);
+    }
+  }
+  if (profile) for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+  return NWK_OK;
+}
+
+int tc_debug_tile(const float* base, long long nb, const float* query, long long nq, int d, long long b0,
+                  long long q0, float* out, cudaStream_t s) {
+  if (d % 4 != 0 || b0 % TB != 0 || q0 % TQ != 0) return fail(NWK_ERR_ARG, "debug tile: bad alignment");
+  NWK_TRY(tc_optin());
+  CUtensorMap tm_q, tm_b;
+  NWK_TRY(make_tmap(&tm_q, query, nq, d, TQ));
+  NWK_TRY(make_tmap(&tm_b, base, nb, d, TB));
+  int* err = nullptr;
+  NWK_CUDA(cudaMalloc(&err, 4));
+  NWK_CUDA(cudaMemsetAsync(err, 0, 4, s));
+  TcParams p{};
+  p.d = d; p.nKB = (d + BK - 1) / BK; p.nq = nq; p.nb = nb;
+  p.nQT = (int)((nq + TQ - 1) / TQ); p.nT = (int)((nb + TB - 1) / TB);
+  p.dump = out; p.dump_qt = (int)(q0 / TQ); p.dump_t = (int)(b0 / TB); p.err = err;
+  tc_kernel<MODE_DUMP><<<1, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+  NWK_LAUNCH_CHECK();
+  int h = 0;
+  NWK_CUDA(cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, s));
+  NWK_CUDA(cudaStreamSynchronize(s));
+  cudaFree(err);
+  if (h != 0) return fail(NWK_ERR_INTERNAL, "tcgen05 pipeline watchdog expired (role code %d)", h);
+  return NWK_OK;
+}
+
+}  // namespace nwk

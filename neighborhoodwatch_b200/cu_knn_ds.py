@@ -1,0 +1,250 @@
+"""Dataset-API (streaming) kNN driver: the entry point of neighborhoodwatch/cu_knn_ds.py.
+
+``compute_knn_ds`` keeps the reference signature (cu_knn_ds.py:136-146) and its output
+contract -- it writes ``partial/final_distances.parquet`` / ``partial/final_indices.parquet``
+directly (cu_knn_ds.py:232-233), so ``merge_indices_and_distances`` afterwards finds no
+numbered partials and returns (merge.py:40-42).
+
+It implements the *intended* semantics of that path: one global
+top-k over all base batches.  The reference overwrites the final file with every base batch,
+re-uploads all queries per batch (cu_knn_ds.py:206-211) and mis-offsets short record batches
+(cu_knn_ds.py:192); here the queries stay resident, base record batches are staged into two
+pinned host slabs and copied on a side stream while the previous slab is searched, every
+slab's exact top-k is folded into a running device-side state (``nwk_topk_state``), offsets
+are the true global row numbers, and the final files are written once.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Iterator, List, Tuple
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.dataset as ds
+import torch
+
+from . import knn as _knn
+from .cu_knn import _device, cleanup, stream_cudf_to_parquet, tune_memory as _tune_table  # noqa: F401
+from .nw_utils import (ensure_partial_dir, get_full_filename, get_partial_distances_filename,
+                       get_partial_indices_filename)
+
+
+def get_gpu_memory():
+    """cu_knn_ds.py:30-36 (GPU of this process instead of the hard-coded index 0)."""
+    return int(torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory)
+
+
+def load_dataset(data_dir, filename):
+    """cu_knn_ds.py:108-110."""
+    return ds.dataset(get_full_filename(data_dir, filename), format="parquet")
+
+
+def dataset_count(dataset):
+    """cu_knn_ds.py:118-119."""
+    return dataset.count_rows()
+
+
+def get_dataset_columns(dataset, n):
+    """cu_knn_ds.py:122-133, without the UnboundLocalError when neither text column exists.
+
+    The reference keeps a text column only to drop it again with ``select_dtypes``
+    (cu_knn_ds.py:195,208); only the embedding columns are returned here.
+    """
+    return [f"embedding_{i}" for i in range(n)]
+
+
+def tune_memory(dataset, batch_size, max_memory_threshold, rmm=None, column_names=None):
+    """cu_knn_ds.py:57-105 on arithmetic (see cu_knn.tune_memory); never raises."""
+    try:
+        import math
+        num_rows = dataset_count(dataset)
+        names = column_names or [n for n in dataset.schema.names if n.startswith("embedding_")]
+        bytes_per_row = max(sum(dataset.schema.field(n).type.bit_width // 8 for n in names
+                                if pa.types.is_primitive(dataset.schema.field(n).type)), 1)
+        total = get_gpu_memory()
+        memory_used = min(num_rows, batch_size) * bytes_per_row
+        factor = math.ceil((total * max_memory_threshold) / max(memory_used, 1))
+        batch_size *= factor
+        while True:
+            if num_rows < batch_size:
+                batch_size = num_rows
+                break
+            if int(batch_size) * bytes_per_row > max_memory_threshold * total:
+                batch_size = int(0.8 * batch_size)
+                break
+            batch_size *= 1.2
+        return int(batch_size)
+    except Exception as e:  # noqa: BLE001
+        print(f"-- exception {e}, max {int(0.8 * batch_size)}")
+        return int(0.8 * batch_size)
+
+
+def _iter_slabs(dataset, columns: List[str], limit: int, slab_rows: int) -> Iterator[Tuple[int, int, List[pa.RecordBatch]]]:
+    """Yield (global_row_offset, rows, record batches) covering exactly ``slab_rows`` rows
+    each (the last one shorter), for the first ``limit`` rows of the dataset."""
+    pending: List[pa.RecordBatch] = []
+    have = 0
+    start = 0
+    seen = 0
+    for batch in dataset.to_batches(columns=columns, batch_size=min(slab_rows, 131072)):
+        if seen >= limit:
+            break
+        if seen + len(batch) > limit:
+            batch = batch.slice(0, limit - seen)
+        seen += len(batch)
+        while len(batch):
+            take = min(len(batch), slab_rows - have)
+            pending.append(batch.slice(0, take))
+            have += take
+            batch = batch.slice(take)
+            if have == slab_rows:
+                yield start, have, pending
+                start += have
+                pending, have = [], 0
+    if have:
+        yield start, have, pending
+
+
+def _fill_pinned(staging: np.ndarray, batches: List[pa.RecordBatch], columns: List[str]) -> None:
+    """Column-per-dimension record batches -> column-major ``[d, rows]`` pinned staging."""
+    off = 0
+    for b in batches:
+        n = len(b)
+        for j, name in enumerate(columns):
+            staging[j, off:off + n] = b.column(b.schema.get_field_index(name)).to_numpy(zero_copy_only=False)
+        off += n
+
+
+def compute_knn_ds(data_dir,
+                   dimensions,
+                   query_filename,
+                   query_count,
+                   base_filename,
+                   base_count,
+                   mem_tune=False,
+                   k=100,
+                   initial_batch_size=200000,
+                   max_memory_threshold=0.2,
+                   split=True):
+    """cu_knn_ds.py:136-178."""
+    device = _device()
+    batch_size = initial_batch_size
+    query_dataset = load_dataset(data_dir, query_filename)
+    query_column_names = get_dataset_columns(query_dataset, dimensions)
+    base_dataset = load_dataset(data_dir, base_filename)
+    base_column_names = get_dataset_columns(base_dataset, dimensions)
+    for name in base_column_names:
+        assert name in base_dataset.schema.names, f"base file lacks column {name}"
+    for name in query_column_names:
+        assert name in query_dataset.schema.names, f"query file lacks column {name}"
+    base_count = min(base_count, dataset_count(base_dataset))
+    query_count = min(query_count, dataset_count(query_dataset))
+
+    if mem_tune:
+        batch_size = tune_memory(base_dataset, batch_size, max_memory_threshold, None, base_column_names)
+    batch_size = int(min(batch_size, base_count))
+
+    # cu_knn_ds.py:168
+    assert (base_count % batch_size == 0) or k <= (base_count % batch_size), \
+        f"Cannot generate k of {k} with only {base_count} rows and batch_size of {batch_size}."
+
+    process_dataset_batches(data_dir, base_dataset, base_column_names, query_dataset, query_column_names,
+                            batch_size, query_count, k, split, base_count=base_count, device=device)
+
+
+def process_dataset_batches(data_dir,
+                            base_dataset,
+                            base_column_names,
+                            query_dataset,
+                            query_column_names,
+                            batch_size,
+                            query_count,
+                            k,
+                            split,
+                            base_count=None,
+                            device=None):
+    """cu_knn_ds.py:181-239 with a running global top-k and a double-buffered loader."""
+    device = device or _device()
+    ensure_partial_dir(data_dir)
+    if base_count is None:
+        base_count = dataset_count(base_dataset)
+    d = len(base_column_names)
+
+    # queries: resident for the whole run
+    q_table = query_dataset.head(query_count, columns=query_column_names)
+    q_stage = torch.empty((d, len(q_table)), dtype=torch.float32, pin_memory=True)
+    _fill_pinned(q_stage.numpy(), q_table.to_batches(), query_column_names)
+    queries = q_stage.to(device).t().contiguous()
+    nq = queries.shape[0]
+    assert nq == query_count                                        # cu_knn_ds.py:229-230
+
+    copy_stream = torch.cuda.Stream(device=device)
+    staging = [torch.empty((d, batch_size), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    staged_evt = [torch.cuda.Event() for _ in range(2)]
+    dev_cm = [torch.empty((d, batch_size), dtype=torch.float32, device=device) for _ in range(2)]
+    state = _knn.RunningTopK(nq, k, device) if base_count > batch_size else None
+    result = None
+
+    slabs = _iter_slabs(base_dataset, base_column_names, base_count, batch_size)
+    # a reader thread decodes parquet into the pinned slab while the GPU works
+    lock = threading.Semaphore(2)
+    ready: list = []
+    done = threading.Event()
+    cond = threading.Condition()
+    error: list = []
+
+    def reader():
+        # decodes parquet into the pinned slab AND enqueues its host->device copy, so the copy
+        # of slab i+1 runs on the side stream while the main thread is inside knn(slab i)
+        try:
+            torch.cuda.set_device(device)
+            for i, (offset, rows, batches) in enumerate(slabs):
+                lock.acquire()                      # slot b is free: knn(slab i-2) has returned
+                b = i & 1
+                _fill_pinned(staging[b].numpy(), batches, base_column_names)
+                with torch.cuda.stream(copy_stream):
+                    dev_cm[b][:, :rows].copy_(staging[b][:, :rows], non_blocking=True)
+                    staged_evt[b].record(copy_stream)
+                with cond:
+                    ready.append((i, offset, rows))
+                    cond.notify()
+        except Exception as e:  # noqa: BLE001
+            error.append(e)
+        finally:
+            done.set()
+            with cond:
+                cond.notify()
+
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    main_stream = torch.cuda.current_stream(device)
+    while True:
+        with cond:
+            while not ready and not done.is_set():
+                cond.wait(0.05)
+            if not ready:
+                break
+            i, offset, rows = ready.pop(0)
+        b = i & 1
+        main_stream.wait_event(staged_evt[b])
+        dataset = dev_cm[b][:, :rows].t().contiguous()
+        if split:
+            assert (k <= len(dataset))                              # cu_knn_ds.py:204
+        dist, idx = _knn.knn(dataset, queries, k, metric="sqeuclidean", id_offset=offset)
+        if state is not None:
+            state.update(dist, idx)
+        else:
+            result = (dist, idx)
+        lock.release()
+    th.join()
+    if error:
+        raise error[0]
+    if state is not None:
+        result = state.result()
+        torch.cuda.current_stream(device).synchronize()
+        state.close()
+    distances, indices = result
+    assert (len(distances) == query_count)                          # cu_knn_ds.py:229
+    assert (len(indices) == query_count)                            # cu_knn_ds.py:230
+    stream_cudf_to_parquet(get_partial_distances_filename(data_dir, -1), distances, 100000)
+    stream_cudf_to_parquet(get_partial_indices_filename(data_dir, -1), indices, 100000)

@@ -1,0 +1,213 @@
+"""Array-level operators: the calls the reference makes into RAPIDS / torch, served by libnwk.
+
+``knn(dataset, queries, k)`` has the signature and result convention of
+``pylibraft.neighbors.brute_force.knn`` as the reference uses it
+(neighborhoodwatch/cu_knn.py:243-245, cu_knn_ds.py:213): row-major fp32 device arrays in,
+``(distances f32[nq,k], indices i64[nq,k])`` out, ascending per row, indices local to
+``dataset``.  The ``metric`` keyword selects what the reference selects with ``engine``
+(cu_knn.py:242-262).
+
+PyTorch is only the owner of device memory and streams here; every kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+
+ENGINE_METRIC = {"raft": "sqeuclidean", "cuvs": "cosine", "torch": "dot"}   # cu_knn.py:242-262
+_ws_cache: dict = {}
+last_stats: Optional[dict] = None
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """One grow-only scratch tensor per device (the caller owns scratch, include/nwk.h)."""
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _ws_cache.pop(key, None)
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def release_workspace() -> None:
+    _ws_cache.clear()
+
+
+def _as_f32_cuda(x: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device")
+    if x.device.type != "cuda":
+        raise RuntimeError(f"{name} is on {x.device}; this engine has no CPU path")
+    if x.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, d]")
+    # the reference feeds `.astype(np.float32)` C-order arrays (cu_knn.py:243-244)
+    return x.to(torch.float32).contiguous()
+
+
+def knn(dataset: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "sqeuclidean",
+        id_offset: int = 0, force_exact_scan: bool = False, no_fallback: bool = False, profile: bool = False,
+        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact k nearest neighbours; drop-in for brute_force.knn(dataset, queries, k)."""
+    global last_stats
+    lib = _native.load()
+    dataset = _as_f32_cuda(dataset, "dataset")
+    queries = _as_f32_cuda(queries, "queries")
+    if dataset.shape[1] != queries.shape[1]:
+        raise ValueError(f"dimension mismatch: dataset d={dataset.shape[1]}, queries d={queries.shape[1]}")
+    if dataset.device != queries.device:
+        raise ValueError("dataset and queries must live on the same device")
+    # cu_knn.py:237 -- `assert (k <= len(dataset))`
+    assert k <= len(dataset), f"k={k} exceeds dataset rows {len(dataset)}"
+    metric_id = _native.METRIC_IDS[metric]
+    nb, d = dataset.shape
+    nq = queries.shape[0]
+    dev = dataset.device
+    flags = ((_native.FLAG_FORCE_EXACT_SCAN if force_exact_scan else 0) | (_native.FLAG_NO_FALLBACK if no_fallback else 0)
+             | (_native.FLAG_PROFILE if profile else 0))
+    with torch.cuda.device(dev):
+        if out is None:
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        else:
+            out_d, out_i = out
+            assert out_d.shape == (nq, k) and out_i.shape == (nq, k) and out_d.is_contiguous() and out_i.is_contiguous()
+        if nq == 0:
+            return out_d, out_i
+        ws_bytes = lib.nwk_knn_workspace_bytes(nb, nq, d, k, metric_id, flags)
+        ws = _workspace(ws_bytes, dev)
+        stats = _native.KnnStats()
+        rc = lib.nwk_knn_f32(dataset.data_ptr(), nb, queries.data_ptr(), nq, d, k, metric_id, int(id_offset),
+                             out_d.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                             ctypes.byref(stats), _stream_ptr(dev))
+        _native.check(rc)
+        last_stats = stats.as_dict()
+    return out_d, out_i
+
+
+def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge ``[P, nq, k_in]`` sorted partial lists into ``[nq, k]`` by (distance, index).
+
+    Device version of the argsort fold at neighborhoodwatch/merge.py:73-104.
+    """
+    lib = _native.load()
+    if dist.device.type != "cuda":
+        raise RuntimeError("merge_topk needs CUDA tensors; this engine has no CPU path")
+    assert dist.dim() == 3 and idx.shape == dist.shape
+    dist = dist.to(torch.float32).contiguous()
+    idx = idx.to(torch.int64).contiguous()
+    P, nq, k_in = dist.shape
+    dev = dist.device
+    with torch.cuda.device(dev):
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if nq == 0:
+            return out_d, out_i
+        ws_bytes = lib.nwk_merge_workspace_bytes(P, nq, k_in, k)
+        ws = _workspace(ws_bytes, dev)
+        rc = lib.nwk_merge_topk(P, dist.data_ptr(), idx.data_ptr(), nq, k_in, k, out_d.data_ptr(),
+                                out_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _native.check(rc)
+    return out_d, out_i
+
+
+class RunningTopK:
+    """Running per-query top-k across base slabs (nwk_topk_state_*), see include/nwk.h."""
+
+    def __init__(self, nq: int, k: int, device: torch.device):
+        self._lib = _native.load()
+        self.nq, self.k, self.device = nq, k, torch.device(device)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.nwk_topk_state_create(nq, k, ctypes.byref(self._handle)))
+
+    def update(self, dist: torch.Tensor, idx: torch.Tensor) -> None:
+        assert dist.shape == (self.nq, self.k) and idx.shape == (self.nq, self.k)
+        dist = dist.to(torch.float32).contiguous()
+        idx = idx.to(torch.int64).contiguous()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.nwk_topk_state_update(self._handle, dist.data_ptr(), idx.data_ptr(),
+                                                          _stream_ptr(self.device)))
+            # keep the inputs alive until the enqueued copies have run
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        with torch.cuda.device(self.device):
+            out_d = torch.empty((self.nq, self.k), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((self.nq, self.k), dtype=torch.int64, device=self.device)
+            _native.check(self._lib.nwk_topk_state_finalize(self._handle, out_d.data_ptr(), out_i.data_ptr(),
+                                                            _stream_ptr(self.device)))
+        return out_d, out_i
+
+    def close(self) -> None:
+        if self._handle:
+            self._lib.nwk_topk_state_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def knn_host(base, queries, k: int, metric: str = "sqeuclidean", id_offset: int = 0, slab_rows: int = 0,
+             out=None):
+    """Host-buffer entry point (nwk_knn_host_f32): numpy / pinned-torch arrays in, numpy out.
+
+    The base is streamed through a two-deep device ring on a side stream while the previous
+    slab is searched -- the loader design for bases that exceed HBM (cu_knn_ds.py:181-239).
+    """
+    global last_stats
+    import numpy as np
+    lib = _native.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("knn_host needs a CUDA device; this engine has no CPU path")
+
+    def host_ptr(a):
+        if isinstance(a, torch.Tensor):
+            assert a.device.type == "cpu" and a.dtype == torch.float32 and a.is_contiguous()
+            return a.data_ptr(), tuple(a.shape)
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a.ctypes.data, a.shape, a
+
+    bp = host_ptr(base)
+    qp = host_ptr(queries)
+    (nb, d), (nq, d2) = bp[1], qp[1]
+    assert d == d2
+    assert k <= nb, f"k={k} exceeds dataset rows {nb}"
+    if out is None:
+        out_d = np.empty((nq, k), dtype=np.float32)
+        out_i = np.empty((nq, k), dtype=np.int64)
+    else:
+        out_d, out_i = out
+        assert out_d.shape == (nq, k) and out_d.dtype == np.float32 and out_d.flags.c_contiguous
+        assert out_i.shape == (nq, k) and out_i.dtype == np.int64 and out_i.flags.c_contiguous
+    stats = _native.KnnStats()
+    rc = lib.nwk_knn_host_f32(bp[0], nb, qp[0], nq, d, k, _native.METRIC_IDS[metric], int(id_offset),
+                              int(slab_rows), out_d.ctypes.data, out_i.ctypes.data, 0, ctypes.byref(stats))
+    _native.check(rc)
+    last_stats = stats.as_dict()
+    return out_d, out_i
+
+
+def debug_tc_tile(dataset: torch.Tensor, queries: torch.Tensor, b0: int, q0: int) -> torch.Tensor:
+    """Raw TF32 tensor-core dot products of one 128x256 tile pair (descriptor validation)."""
+    lib = _native.load()
+    dataset = _as_f32_cuda(dataset, "dataset")
+    queries = _as_f32_cuda(queries, "queries")
+    dev = dataset.device
+    with torch.cuda.device(dev):
+        out = torch.zeros((128, 256), dtype=torch.float32, device=dev)
+        rc = lib.nwk_debug_tc_tile(dataset.data_ptr(), dataset.shape[0], queries.data_ptr(), queries.shape[0],
+                                   dataset.shape[1], b0, q0, out.data_ptr(), _stream_ptr(dev))
+        _native.check(rc)
+    return out

@@ -1,0 +1,220 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (libnwk.so).  -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+from neighborhoodwatch_b200 import synth
+from oracle import knn_oracle as ko
+from oracle import merge_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = {"sqeuclidean": "raft", "cosine": "cuvs", "dot": "torch"}
+
+
+def _dev(arr, device):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+
+
+def _check(got_d, got_i, base, q, k, metric, id_offset=0):
+    t_d, t_i = ko.knn_f64(base, q, k, metric, return_f64=True)
+    # north_star tolerances: distances 1e-5 relative (abs floor 1e-6), ids exact except ties < 1e-6 rel
+    return ko.compare_knn(got_d.cpu().numpy(), got_i.cpu().numpy(), base, q, metric, t_d, t_i + id_offset,
+                          rtol=1e-5, atol=1e-6, tie_rtol=1e-6, id_offset=id_offset)
+
+
+def test_synth_bit_identical(cuda_device):
+    for rows, d, seed, row0 in [(257, 384, 1234, 0), (100, 100, 5678, 12345), (3, 1536, 9, 10 ** 8)]:
+        dev = synth.device_vectors(rows, d, seed, row0, device=cuda_device).cpu().numpy()
+        ref = synth.vectors(rows, d, seed, row0)
+        assert np.array_equal(dev.view(np.uint32), ref.view(np.uint32))
+    raw = synth.device_vectors(10, 16, 3, normalize=False, device=cuda_device).cpu().numpy()
+    assert np.array_equal(raw, synth.vectors(10, 16, 3, normalize=False))
+
+
+@pytest.mark.parametrize("metric", ko.METRICS)
+@pytest.mark.parametrize("nq,nb,d,k", [(37, 1000, 96, 10), (8, 4097, 33, 100), (1, 100, 7, 100), (130, 9000, 128, 100)])
+def test_exact_scan_parity(cuda_device, metric, nq, nb, d, k):
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(nb, d, 1234)
+    q = synth.vectors(nq, d, 5678)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric, id_offset=77,
+                           force_exact_scan=True)
+    assert knn.last_stats["path"] == 0
+    res = _check(got_d, got_i, base, q, k, metric, id_offset=77)
+    assert res["index_mismatches_tied"] == 0      # the fp64 scan has the oracle's arithmetic
+
+
+def test_tc_tile_matches_tf32_model(cuda_device):
+    """Validates TMA map, UMMA descriptors and TMEM read-back in isolation."""
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(0)
+    for d in (32, 64, 384, 100):
+        base = rng.standard_normal((600, d)).astype(np.float32)
+        q = rng.standard_normal((300, d)).astype(np.float32)
+        out = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 256, 128).cpu().numpy()
+        exact = q[128:256].astype(np.float64) @ base[256:512].astype(np.float64).T
+        scale = np.abs(q[128:256].astype(np.float64)) @ np.abs(base[256:512].astype(np.float64)).T
+        err = np.abs(out - exact)
+        c = 2.0 ** -9 * 1.001 + d / 2.0 ** 22
+        assert np.all(err <= c * scale + 1e-6), f"d={d}: max err ratio {(err / (c * scale + 1e-6)).max()}"
+        # rows beyond the inputs read as zero (TMA out-of-bounds fill)
+        out2 = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 512, 256).cpu().numpy()
+        assert np.all(out2[300 - 256:] == 0) and np.all(out2[:, 600 - 512:] == 0)
+
+
+@pytest.mark.parametrize("metric", ko.METRICS)
+@pytest.mark.parametrize("nq,nb,d,k", [
+    (1000, 10000, 384, 100),     # BASELINE config 1
+    (333, 5003, 100, 100),       # ragged everything, d not a multiple of 32
+    (5, 150, 64, 100),           # tiny base: everything is logged, no sampling
+    (129, 2049, 768, 10),        # one row past a tile boundary on both sides
+    (64, 40000, 128, 256),       # k at the tensor-core path's limit
+])
+def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(nb, d, 1234)
+    q = synth.vectors(nq, d, 5678)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric, id_offset=5)
+    st = dict(knn.last_stats)
+    assert st["path"] == 1, st
+    res = _check(got_d, got_i, base, q, k, metric, id_offset=5)
+    assert st["n_fallback_queries"] <= max(1, nq // 100), st
+    print(metric, (nq, nb, d, k), st, res)
+
+
+def test_tc_gaussian_unnormalised(cuda_device):
+    """Non-unit, signed vectors: norms matter for sq-L2 / cosine ordering."""
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(5)
+    base = (rng.standard_normal((20000, 256)) * rng.uniform(0.5, 2.0, (20000, 1))).astype(np.float32)
+    q = rng.standard_normal((200, 256)).astype(np.float32)
+    for metric in ko.METRICS:
+        got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric=metric)
+        assert knn.last_stats["path"] == 1
+        _check(got_d, got_i, base, q, 100, metric)
+
+
+def test_tc_duplicates_fall_back_and_stay_exact(cuda_device):
+    """Many exact duplicates near the k-th: the candidate band cannot be certified; the fp64
+    scan must take over and ties must come out in index order."""
+    from neighborhoodwatch_b200 import knn
+    uniq = synth.vectors(40, 64, 77)
+    base = np.tile(uniq, (200, 1))                       # 8000 rows, each vector 200 times
+    q = synth.vectors(16, 64, 78)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric="sqeuclidean")
+    st = dict(knn.last_stats)
+    t_d, t_i = ko.knn_f64(base, q, 100, "sqeuclidean", return_f64=True)
+    np.testing.assert_array_equal(got_i.cpu().numpy(), t_i)
+    np.testing.assert_allclose(got_d.cpu().numpy(), t_d, rtol=1e-5, atol=1e-6)
+    print(st)
+
+
+def test_uncertifiable_queries_take_the_fp64_scan(cuda_device):
+    """One huge-norm outlier row inflates the proven TF32 error bound beyond the logging
+    threshold: no query can be certified, every one must be recomputed by the fp64 scan."""
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(6000, 64, 1234).copy()
+    base[17] *= 1000.0
+    q = synth.vectors(40, 64, 5678)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric="sqeuclidean")
+    st = dict(knn.last_stats)
+    assert st["path"] == 1 and st["n_fallback_queries"] == 40, st
+    res = _check(got_d, got_i, base, q, 100, "sqeuclidean")
+    assert res["index_mismatches_tied"] == 0
+
+
+def test_merge_parity(cuda_device):
+    import torch
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(1)
+    for P, nq, k_in, k in [(2, 50, 100, 100), (9, 333, 100, 100), (64, 17, 100, 100), (3, 10, 7, 5), (50, 9, 100, 1000)]:
+        k = min(k, P * k_in)
+        d = np.sort(rng.random((P, nq, k_in)).astype(np.float32), axis=2)
+        i = rng.permutation(P * nq * k_in).astype(np.int64).reshape(P, nq, k_in)
+        out_d, out_i = knn.merge_topk(torch.from_numpy(d).to(cuda_device), torch.from_numpy(i).to(cuda_device), k)
+        ref_d, ref_i = mo.merge_by_distance_then_index([(d[p], i[p]) for p in range(P)], k)
+        np.testing.assert_array_equal(out_d.cpu().numpy(), ref_d)
+        np.testing.assert_array_equal(out_i.cpu().numpy(), ref_i)
+    # ties: equal distances resolve by index (deterministic, unlike np.argsort in merge.py:83)
+    d = np.zeros((4, 3, 10), dtype=np.float32)
+    i = rng.permutation(120).astype(np.int64).reshape(4, 3, 10)
+    out_d, out_i = knn.merge_topk(torch.from_numpy(d).to(cuda_device), torch.from_numpy(i).to(cuda_device), 10)
+    for r in range(3):
+        assert list(out_i[r].cpu().numpy()) == sorted(i[:, r, :].ravel())[:10]
+
+
+def test_running_topk_equals_one_shot(cuda_device):
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(6000, 64, 1234)
+    q = synth.vectors(100, 64, 5678)
+    bd, qd = _dev(base, cuda_device), _dev(q, cuda_device)
+    st = knn.RunningTopK(100, 20, cuda_device)
+    for lo in range(0, 6000, 1500):
+        d, i = knn.knn(bd[lo:lo + 1500], qd, 20, metric="sqeuclidean", id_offset=lo)
+        st.update(d, i)
+    rd, ri = st.result()
+    _check(rd, ri, base, q, 20, "sqeuclidean")
+    st.close()
+
+
+def test_host_entry_point(cuda_device):
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(30000, 128, 1234)
+    q = synth.vectors(300, 128, 5678)
+    import torch
+    out_d, out_i = knn.knn_host(base, q, 100, metric="cosine", slab_rows=7000)     # 5 slabs, ragged last
+    _check(torch.from_numpy(out_d), torch.from_numpy(out_i), base, q, 100, "cosine")
+    out_d, out_i = knn.knn_host(base, q, 100, metric="dot")                          # one slab
+    _check(torch.from_numpy(out_d), torch.from_numpy(out_i), base, q, 100, "dot")
+
+
+def test_error_behaviour(cuda_device):
+    from neighborhoodwatch_b200 import _native, knn
+    import torch
+    base = _dev(synth.vectors(50, 16, 1), cuda_device)
+    q = _dev(synth.vectors(5, 16, 2), cuda_device)
+    with pytest.raises(AssertionError):              # cu_knn.py:237
+        knn.knn(base, q, 51)
+    with pytest.raises(RuntimeError):
+        knn.knn(base.cpu(), q.cpu(), 5)              # no CPU path
+    lib = _native.load()
+    rc = lib.nwk_knn_f32(base.data_ptr(), 50, q.data_ptr(), 5, 16, 10, 0, 0, q.data_ptr(), q.data_ptr(), None, 0, 0,
+                         None, None)
+    assert rc == 3 and b"workspace" in lib.nwk_last_error()
+    d, i = knn.knn(base, q[:0], 5)
+    assert d.shape == (0, 5)
+
+
+def test_large_shape_properties(cuda_device):
+    """BASELINE config-2 arithmetic (d=768, cosine) at a size whose truth the oracle still
+    computes in seconds for a sample of queries; the rest is checked against the on-device
+    fp64 scan and through size-independent properties."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    nq, nb, d, k = 2048, 200_000, 768, 100
+    bd = synth.device_vectors(nb, d, 1234, device=cuda_device)
+    qd = synth.device_vectors(nq, d, 5678, device=cuda_device)
+    got_d, got_i = knn.knn(bd, qd, k, metric="cosine")
+    st = dict(knn.last_stats)
+    assert st["path"] == 1
+    assert torch.all(got_d[:, 1:] >= got_d[:, :-1])                       # ascending (merge.py:104)
+    assert int(got_i.min()) >= 0 and int(got_i.max()) < nb
+    srt = torch.sort(got_i, dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1])                           # no repeated neighbour
+    sel = torch.arange(0, nq, 16, device=cuda_device)                     # 128 sampled queries
+    ex_d, ex_i = knn.knn(bd, qd[sel], k, metric="cosine", force_exact_scan=True)
+    assert torch.equal(ex_i, got_i[sel]) and torch.equal(ex_d, got_d[sel])
+    # oracle truth for 32 of them
+    base = synth.vectors(nb, d, 1234)
+    q = synth.vectors(nq, d, 5678)[::64]
+    _check(got_d[::64], got_i[::64], base, q, k, "cosine")
+    # sharding property: top-k of the union == merge of the shards' top-k
+    parts = [knn.knn(bd[lo:lo + 50_000], qd[:256], k, metric="cosine", id_offset=lo) for lo in range(0, nb, 50_000)]
+    m_d, m_i = knn.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert torch.equal(m_d, got_d[:256])
+    same = (m_i == got_i[:256])
+    assert float(same.float().mean()) > 0.9999      # only fp32-equal distances may swap
+    print(st)
