@@ -282,8 +282,12 @@ def main():
         t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if distributed:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e_i_t = torch.as_tensor(e_i)
-        same = bool(torch.equal(e_i_t.to(dev), out_i))
+        # slab results are merged by (fp32 distance, id), the resident result is ordered by
+        # (fp64 distance, id): compare distances exactly and ids as per-row sets
+        e_i_t = torch.as_tensor(e_i).to(dev)
+        e_d_t = torch.as_tensor(e_d).to(dev)
+        same = bool(torch.equal(e_d_t, out_d)) and bool(
+            torch.equal(torch.sort(e_i_t, dim=1).values, torch.sort(out_i, dim=1).values))
         e2e = {"value": nq * nb_total * args.e2e_steps / float(t_e2e.item()), "unit": "pairs/s",
                "h2d_bytes_per_step": (nb_local * d * 4 + nq * d * 4) * n_gpus,
                "d2h_bytes_per_step": nq * k * 12 * n_gpus, "steps": args.e2e_steps,

@@ -215,6 +215,14 @@ def test_large_shape_properties(cuda_device):
     parts = [knn.knn(bd[lo:lo + 50_000], qd[:256], k, metric="cosine", id_offset=lo) for lo in range(0, nb, 50_000)]
     m_d, m_i = knn.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
     assert torch.equal(m_d, got_d[:256])
-    same = (m_i == got_i[:256])
-    assert float(same.float().mean()) > 0.9999      # only fp32-equal distances may swap
+    # the merge orders by (fp32 distance, id), the one-shot result by (fp64 distance, id): ids may
+    # differ only inside runs of fp32-equal distances, and each row must hold the same id set
+    diff = (m_i != got_i[:256])
+    assert torch.equal(torch.sort(m_i, dim=1).values, torch.sort(got_i[:256], dim=1).values)
+    left = torch.zeros_like(diff)
+    left[:, 1:] = m_d[:, 1:] == m_d[:, :-1]
+    right = torch.zeros_like(diff)
+    right[:, :-1] = m_d[:, :-1] == m_d[:, 1:]
+    assert bool(torch.all(~diff | left | right))
+    assert float(diff.float().mean()) < 5e-3
     print(st)
