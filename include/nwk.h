@@ -60,19 +60,20 @@ typedef enum nwk_metric {
 #define NWK_FLAG_FORCE_EXACT_SCAN 0x1u /* skip the tensor-core candidate stage; fp64 scan of every pair */
 #define NWK_FLAG_NO_FALLBACK      0x2u /* do not run the fp64 scan for uncertified queries (diagnostics) */
 #define NWK_FLAG_PROFILE          0x4u /* bracket each stage with CUDA events on `stream`; fills stats->ms_*  */
+#define NWK_FLAG_TF32             0x8u /* candidate stage on fp32 operands as TF32 (no fp16 staging copy)      */
 
 /* Per-call diagnostics (all counters refer to the last nwk_knn_f32 call they were passed to). */
 typedef struct nwk_knn_stats {
-  int32_t path;               /* 0 = fp64 exact scan, 1 = tcgen05 TF32 candidates + fp64 rerank          */
+  int32_t path;               /* 0 = fp64 exact scan; tcgen05 candidates + fp64 rerank: 1 = fp16, 2 = TF32 */
   int32_t n_fallback_queries; /* queries whose candidate set could not be certified -> fp64 exact scan   */
   int32_t max_candidates;     /* largest per-query candidate-log population seen                         */
   int32_t max_rerank;         /* largest per-query number of rows re-ranked in fp64                      */
   int64_t total_candidates;   /* sum over queries of candidate-log population                            */
   int64_t total_rerank;       /* sum over queries of rows re-ranked in fp64                              */
   int32_t gpu_launches;       /* kernels launched by this call                                           */
-  int32_t reserved;
+  float   max_err_ratio;      /* max |candidate key - exact key| / proven bound over re-ranked rows (<= 1) */
   /* device time per stage, CUDA events on the caller's stream; 0 unless NWK_FLAG_PROFILE */
-  float   ms_rownorm;         /* base row norms (HBM-bound)                                              */
+  float   ms_prep;            /* operand preparation: norms, alpha/beta, fp16 staging copy (HBM-bound)   */
   float   ms_sample;          /* tcgen05 sample pass -> per-query thresholds                             */
   float   ms_filter;          /* tcgen05 filter pass over the whole base: the dominant kernel            */
   float   ms_finish;          /* select + fp64 rerank                                                    */
@@ -102,7 +103,8 @@ int64_t nwk_launch_count(void);
  *   workspace device scratch of at least nwk_knn_workspace_bytes(...) bytes, 256-byte aligned
  *   stats     optional (may be NULL), HOST memory
  *
- * Results are exact: candidates are produced on the tensor cores in TF32, every candidate
+ * Results are exact: candidates are produced on the tensor cores (fp16 operands scaled by
+ * exact powers of two -- the significand width of TF32 -- or TF32 itself), every candidate
  * within a proven error bound of the k-th is re-ranked in fp64, and queries for which the
  * bound cannot be established are recomputed by an fp64 scan.  Ordering is by
  * (fp64 distance, index).  Fails with NWK_ERR_ARG when k > nb (the reference asserts
@@ -159,11 +161,11 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
 int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0,
                    int32_t normalize, void* stream);
 
-/* Diagnostics used by the parity tests: raw TF32 tensor-core dot products of one
+/* Diagnostics used by the parity tests: raw tensor-core dot products (fp16 or TF32 operands) of one
  * 128 x 256 tile pair (query rows q0.., base rows b0..) written to out[128*256] fp32,
  * so the tcgen05 / TMA descriptors can be validated in isolation. */
 int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d,
-                      int64_t b0, int64_t q0, float* out, void* stream);
+                      int64_t b0, int64_t q0, float* out, int32_t use_f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ METRIC_IDS = {"sqeuclidean": METRIC_SQEUCLIDEAN, "cosine": METRIC_COSINE, "dot":
 FLAG_FORCE_EXACT_SCAN = 0x1
 FLAG_NO_FALLBACK = 0x2
 FLAG_PROFILE = 0x4
+FLAG_TF32 = 0x8
 MAX_K = 1024
 
 # every symbol include/nwk.h declares (tests/test_abi.py checks the library exports them all)
@@ -40,7 +41,7 @@ class KnnStats(Structure):
     _fields_ = [
         ("path", c_int32), ("n_fallback_queries", c_int32), ("max_candidates", c_int32),
         ("max_rerank", c_int32), ("total_candidates", c_int64), ("total_rerank", c_int64),
-        ("gpu_launches", c_int32), ("reserved", c_int32), ("ms_rownorm", c_float), ("ms_sample", c_float),
+        ("gpu_launches", c_int32), ("max_err_ratio", c_float), ("ms_prep", c_float), ("ms_sample", c_float),
         ("ms_filter", c_float), ("ms_finish", c_float), ("ms_fallback", c_float), ("ms_total", c_float),
     ]
 
@@ -95,7 +96,7 @@ def load() -> ctypes.CDLL:
     lib.nwk_synth_fill.argtypes = [c_void_p, c_int64, c_int32, c_uint64, c_int64, c_int32, c_void_p]
     lib.nwk_debug_tc_tile.restype = c_int32
     lib.nwk_debug_tc_tile.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p,
-                                      c_void_p]
+                                      c_int32, c_void_p]
     if lib.nwk_abi_version() != 1:
         raise ImportError(f"{path}: ABI version {lib.nwk_abi_version()} != 1")
     _lib = lib

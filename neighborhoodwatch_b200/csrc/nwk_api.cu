@@ -22,7 +22,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
            unsigned int flags, nwk_knn_stats* stats, cudaStream_t s);
 int tc_debug_tile(const float* base, long long nb, const float* query, long long nq, int d, long long b0,
-                  long long q0, float* out, cudaStream_t s);
+                  long long q0, float* out, int use_f16, cudaStream_t s);
 int synth_fill(float* out, long long rows, int d, unsigned long long seed, long long row0, int normalize,
                cudaStream_t s);
 
@@ -342,6 +342,7 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
         total.gpu_launches += s1.gpu_launches;
         if (s1.max_candidates > total.max_candidates) total.max_candidates = s1.max_candidates;
         if (s1.max_rerank > total.max_rerank) total.max_rerank = s1.max_rerank;
+        if (s1.max_err_ratio > total.max_err_ratio) total.max_err_ratio = s1.max_err_ratio;
         if (st) NWK_TRY(nwk_topk_state_update(st, c.part_d, (const int64_t*)c.part_i, c.comp_stream));
         return NWK_OK;
       }();
@@ -373,10 +374,10 @@ int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t r
 }
 
 int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int64_t b0,
-                      int64_t q0, float* out, void* stream) {
+                      int64_t q0, float* out, int32_t use_f16, void* stream) {
   if (!base || !query || !out) return fail(NWK_ERR_ARG, "null pointer argument");
   NWK_TRY(device_check());
-  return tc_debug_tile(base, nb, query, nq, d, b0, q0, out, static_cast<cudaStream_t>(stream));
+  return tc_debug_tile(base, nb, query, nq, d, b0, q0, out, use_f16, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

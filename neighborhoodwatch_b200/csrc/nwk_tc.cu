@@ -2,27 +2,38 @@
 //
 // Pipeline of one nwk_knn_f32 call (replaces knn() at cu_knn.py:243-257 of the reference):
 //
-//   rownorm_kernel   per base row j: alpha_j, beta_j so that key(q,j) = alpha_j + beta_j*(q.b_j)
-//                    orders rows like the requested distance (|b|^2 - 2 q.b, -q.b/|b|, -q.b);
-//                    also max |b|.                                     HBM-bound, B*d*4 bytes.
-//   tc_kernel<SAMPLE>  TF32 tcgen05 GEMM of every query tile against a strided sample of base
-//                    tiles; epilogue keeps the m smallest keys per query -> threshold tau_q
-//                    such that about `target` rows of the whole base fall below it.
+//   qmax / qprep     queries -> fp16 with one global power-of-two scale (exact scaling).
+//   baseprep         per base row j: |b_j|^2 in fp64, alpha_j / beta_j so that
+//                    key(q,j) = alpha_j + beta_j * acc(q,j) orders rows like the requested
+//                    distance (|b|^2 - 2 q.b, -q.b/|b|, -q.b); fp16 copy of the row with a
+//                    per-row power-of-two scale (folded into beta_j).  HBM-bound: reads
+//                    B*d*4 bytes, writes B*d*2.
+//   tc_kernel<SAMPLE>  tcgen05 GEMM of every query tile against a strided sample of base
+//                    tiles; the epilogue keeps the 32 smallest keys per query in registers
+//                    -> threshold tau_q with about `target` rows of the whole base below it.
 //   tc_kernel<FILTER>  the same GEMM over the whole base; the epilogue compares each key with
 //                    tau_q straight out of TMEM and appends the (rare) survivors to a
 //                    per-query candidate log.  The distance matrix never reaches HBM.
-//                    Tensor-pipe bound: 2*Q*B*d FLOP.
-//   finish_kernel    per query: sort the log, take every candidate whose TF32 key lies within
-//                    2*eps of the k-th (eps = proven TF32 error bound), recompute those in
-//                    fp64 from the fp32 inputs, order by (distance, index), emit k.
-//                    A query is *certified* when tau_q lies above that band (so no row outside
-//                    the log can belong to the true top-k); the others go to the fp64 scan.
+//                    Tensor-pipe / L2 bound: 2*Q*B*d FLOP.
+//   finish_kernel    per query: sort the log, take every candidate whose approximate key lies
+//                    within 2*eps of the k-th (eps = proven error bound of the fp16 operands),
+//                    recompute those in fp64 from the fp32 inputs, order by (distance, index),
+//                    emit k.  A query is *certified* when tau_q lies above that band (no row
+//                    outside the log can belong to the true top-k); the rest go to the fp64 scan.
+//
+// Operand precision: fp16 has the 11-bit significand of TF32; with exact power-of-two scaling
+// (per base row, global for the queries) every element is a normal fp16 number, so the
+// candidate keys are as accurate as TF32 ones while the tensor pipe runs at twice the TF32
+// rate and the operand tiles are half as large (the kernel is L2->SM bandwidth bound).  The
+// TF32 variant (fp32 operands straight from the caller's buffers, no staging copy) is kept
+// behind NWK_FLAG_TF32.
 //
 // Tile shape: 128 queries (MMA M, one TMEM lane per query) x 256 base rows (MMA N), K-blocks
-// of 32 fp32 = one 128-byte swizzle span, 4-stage TMA ring (48 KB per stage), two TMEM
-// accumulator stages of 256 columns so the epilogue of pair p overlaps the MMAs of pair p+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue.
+// of 128 bytes (= one swizzle span: 64 fp16 / 32 fp32), 4-stage TMA ring (48 KB per stage),
+// two TMEM accumulator stages of 256 columns so the epilogue of pair p overlaps the MMAs of
+// pair p+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -38,30 +49,35 @@ size_t exact_scan_workspace_bytes(long long nb, long long nsel, int k);
 
 constexpr int TQ = 128;
 constexpr int TB = 256;
-constexpr int BK = 32;
-constexpr int UMMA_K = 8;
 constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int TC_THREADS = 256;
-constexpr int STAGE_A_BYTES = TQ * BK * 4;     // 16 KB
-constexpr int STAGE_B_BYTES = TB * BK * 4;     // 32 KB
+constexpr int STAGE_A_BYTES = TQ * 128;        // 16 KB: 128 rows x one 128-byte swizzle span
+constexpr int STAGE_B_BYTES = TB * 128;        // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-constexpr int M_MAX = 32;                      // longest per-query sample list
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + M_MAX * TQ * 4 + 256 + 1024;
-constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
-constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
+constexpr int LOG_CAP = 8192;                  // candidate-log slots per query
+constexpr int LOG_TARGET = 1536;               // population the sampled threshold aims at
+constexpr int RERANK_MAX = 2048;               // most rows re-ranked in fp64 per query
 constexpr int TC_MAX_K = 256;
 constexpr int FIN_THREADS = 256;
 
 enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
 enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
 
+// operand-type traits: elements per 128-byte K-block, K per MMA instruction
+template <bool F16> struct Op {
+  static constexpr int BK = F16 ? 64 : 32;
+  static constexpr int UMMA_K = F16 ? 16 : 8;
+};
+
 struct TcParams {
-  int d, nKB;
+  int nKB;
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
-  int nS, m;                // SAMPLE: sample tiles, list length
+  int nS, sChunks;          // SAMPLE: sample tiles, 32-column chunks used per sample tile
   const float* alpha;       // [nT*TB]
   const float* beta;        // [nT*TB]
   float* tau;               // [nQT*TQ]
@@ -72,14 +88,62 @@ struct TcParams {
   int* err;
 };
 
+struct Scalars {            // one block of device scalars, zeroed per call
+  unsigned int bn2max;      // max |b|^2 (float bits)
+  unsigned int qabsmax;     // max |q_i| (float bits)
+  int err;
+  int fail_cnt;
+  unsigned int stat_max[2];
+  unsigned int err_ratio;   // max |approx key - exact key| / eps over re-ranked rows (float bits)
+  unsigned int pad;
+  unsigned long long stat_sum[2];
+};
+
 // ---------------------------------------------------------------------------------------
-// rownorm: alpha / beta per base row (padded to whole tiles) + max norm
+// operand preparation
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-rownorm_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int metric,
-               float* __restrict__ alpha, float* __restrict__ beta, unsigned int* __restrict__ bn2max) {
+qmax_kernel(const float* __restrict__ q, long long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(q[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < __int_as_float(0x7f800000)) atomicMax(out, __float_as_uint(m));
+}
+
+// power-of-two exponent s such that maxabs * 2^s lies in [2^14, 2^15): every element of the
+// scaled vector is then far inside fp16's range and only elements below 2^-28 * maxabs fall
+// into the subnormal range.
+__device__ __forceinline__ int f16_scale_exp(float maxabs) {
+  if (!(maxabs > 0.f)) return 0;
+  int e;
+  frexpf(maxabs, &e);       // maxabs = m * 2^e, m in [0.5, 1)
+  return 15 - e;
+}
+
+__global__ void __launch_bounds__(256)
+qprep_kernel(const float* __restrict__ q, long long nq, int d, int dh, const Scalars* __restrict__ sc,
+             __half* __restrict__ qh) {
+  const int s = f16_scale_exp(__uint_as_float(sc->qabsmax));
+  const long long n = nq * dh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / dh;
+    int c = (int)(i - r * dh);
+    float v = c < d ? q[r * d + c] : 0.f;
+    qh[i] = __float2half_rn(ldexpf(v, s));
+  }
+}
+
+// one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale
+template <bool F16>
+__global__ void __launch_bounds__(256)
+baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
+                float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
+                __half* __restrict__ bh) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float INF = __int_as_float(0x7f800000);
+  const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
   float local_max = 0.f;
   for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
     if (row >= nb) {
@@ -88,26 +152,48 @@ rownorm_kernel(const float* __restrict__ base, long long nb, long long nb_pad, i
     }
     const float* brow = base + row * d;
     double a = 0.0;
+    float mx = 0.f;
     for (int c = lane * 4; c < d; c += 128) {
       float4 v = __ldg(reinterpret_cast<const float4*>(brow + c));
       a = fma((double)v.x, (double)v.x, a);
       a = fma((double)v.y, (double)v.y, a);
       a = fma((double)v.z, (double)v.z, a);
       a = fma((double)v.w, (double)v.w, a);
+      mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(mx, fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     a = warp_sum(a);
+    int sb = 0;
+    if (F16) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (!(mx < INF)) mx = 0.f;             // inf / nan rows: leave unscaled (they never rank)
+      sb = f16_scale_exp(mx);
+      __half* hrow = bh + row * dh;
+      for (int c = lane * 4; c < dh; c += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) v = __ldg(reinterpret_cast<const float4*>(brow + c));     // d % 4 == 0
+        __half2 h01 = __floats2half2_rn(ldexpf(v.x, sb), ldexpf(v.y, sb));
+        __half2 h23 = __floats2half2_rn(ldexpf(v.z, sb), ldexpf(v.w, sb));
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned int*>(&h01);
+        pk.y = *reinterpret_cast<unsigned int*>(&h23);
+        *reinterpret_cast<uint2*>(hrow + c) = pk;                            // dh % 8 == 0
+      }
+    }
     if (lane == 0) {
-      float al = 0.f, be = -1.f;
-      if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f; }
+      // acc = 2^(sq+sb) * (q.b) up to operand rounding: fold the scale into beta (exact)
+      const float unscale = ldexpf(1.f, -(sq + sb));
+      float al = 0.f, be = -unscale;
+      if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f * unscale; }
       else if (metric == NWK_METRIC_COSINE) {
-        if (a > 0.0) be = (float)(-1.0 / sqrt(a)); else { al = INF; be = 0.f; }
+        if (a > 0.0) be = (float)(-1.0 / sqrt(a)) * unscale; else { al = INF; be = 0.f; }
       }
       alpha[row] = al;
       beta[row] = be;
       local_max = fmaxf(local_max, __double2float_ru(a));
     }
   }
-  if (lane == 0 && local_max > 0.f) atomicMax(bn2max, __float_as_uint(local_max));
+  if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -159,16 +245,17 @@ struct Sched {
   }
 };
 
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
+  constexpr int BK = Op<F16>::BK;
+  constexpr int UMMA_K = Op<F16>::UMMA_K;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_list = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);           // [M_MAX][TQ]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + M_MAX * TQ * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
@@ -221,7 +308,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       int qt, t; bool first, last;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t idesc = ptx::umma_idesc_tf32(TQ, TB);
+      const uint32_t idesc = F16 ? ptx::umma_idesc_f16(TQ, TB) : ptx::umma_idesc_tf32(TQ, TB);
       bool ok = true;
       while (ok && sch.next(qt, t, first, last)) {
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
@@ -235,8 +322,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           const uint64_t db = ptx::umma_desc_sw128(sa + STAGE_A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 8 fp32 = 32 B inside the 128 B swizzle span: +2 in 16-byte units
-            ptx::mma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            // one MMA consumes 32 bytes of K inside the 128 B swizzle span: +2 in 16-byte units
+            if (F16) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else ptx::mma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::tc_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -256,7 +344,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     const float INF = __int_as_float(0x7f800000);
     float tau = -INF;
     long long q = 0;
-    int filled = 0;   // SAMPLE: how many list slots hold real values
+    float lst[SAMPLE_M];      // SAMPLE: ascending list of the smallest keys seen (registers)
     bool ok = true;
     while (ok && sch.next(qt, t, first, last)) {
       if (first) {
@@ -265,8 +353,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           tau = (q < p.nq) ? p.tau[q] : -INF;
         } else if (MODE == MODE_SAMPLE) {
           tau = (q < p.nq) ? INF : -INF;
-          filled = 0;
-          for (int j = 0; j < p.m; ++j) s_list[j * TQ + row_in_tile] = INF;
+#pragma unroll
+          for (int j = 0; j < SAMPLE_M; ++j) lst[j] = INF;
         }
       }
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
@@ -275,15 +363,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       const float4* al4 = reinterpret_cast<const float4*>(p.alpha + (long long)t * TB);
       const float4* be4 = reinterpret_cast<const float4*>(p.beta + (long long)t * TB);
       const long long row0 = (long long)t * TB;
+      const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : TB / 32;
 
       uint32_t va[32], vb[32];
       ptx::tmem_ld_32x32(taddr, va);
 #pragma unroll
       for (int ch = 0; ch < TB / 32; ++ch) {
+        if (MODE == MODE_SAMPLE && ch >= nch) break;      // warp-uniform
         ptx::tmem_wait_ld();
         uint32_t(&cur)[32] = (ch & 1) ? vb : va;
         uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-        if (ch + 1 < TB / 32) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
+        if (ch + 1 < TB / 32 && ch + 1 < nch) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
         if (MODE == MODE_DUMP) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -302,8 +392,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float key = kk[e];
-                if (key < tau) {
-                  if (MODE == MODE_FILTER) {
+                if (MODE == MODE_FILTER) {
+                  if (key < tau) {
                     const unsigned int slot = atomicAdd(p.cnt + q, 1u);
                     if (slot < LOG_CAP) {
                       const unsigned long long rec =
@@ -311,27 +401,28 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
                           static_cast<unsigned long long>(row0 + ch * 32 + j4 * 4 + e);
                       p.log[q * LOG_CAP + slot] = rec;
                     }
-                  } else {
-                    // insertion into the ascending list of the m smallest keys seen
-                    int pos = min(filled, p.m - 1);
-                    while (pos > 0 && s_list[(pos - 1) * TQ + row_in_tile] > key) {
-                      s_list[pos * TQ + row_in_tile] = s_list[(pos - 1) * TQ + row_in_tile];
-                      --pos;
-                    }
-                    s_list[pos * TQ + row_in_tile] = key;
-                    if (filled < p.m) ++filled;
-                    if (filled == p.m) tau = s_list[(p.m - 1) * TQ + row_in_tile];
                   }
+                } else {
+                  // branch-free insertion: bubble the key through the sorted register list
+                  float kx = (key < tau) ? key : INF;
+#pragma unroll
+                  for (int j = 0; j < SAMPLE_M; ++j) {
+                    const float lo = fminf(lst[j], kx);
+                    kx = fmaxf(lst[j], kx);
+                    lst[j] = lo;
+                  }
+                  tau = (q < p.nq) ? lst[SAMPLE_M - 1] : -INF;
                 }
               }
             }
           }
         }
       }
+      ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      if (MODE == MODE_SAMPLE && last && q < p.nq) p.tau[q] = (filled == p.m) ? tau : INF;
+      if (MODE == MODE_SAMPLE && last && q < p.nq) p.tau[q] = tau;
     }
   }
 
@@ -351,12 +442,11 @@ struct FinParams {
   long long nb, nq; int d, k, metric;
   long long id_offset;
   const float* tau; const unsigned int* cnt; const unsigned long long* log;
-  const unsigned int* bn2max;
-  float c_err;                 // TF32 dot-product relative error constant
+  Scalars* sc;
+  float c_rel;                 // relative error constant of the operand format
+  int f16;                     // fp16 operands: adds the subnormal-quantisation term
   float* out_dist; long long* out_idx;
-  int* fail_cnt; int* fail_list;
-  unsigned long long* stat_sum; // [0] sum cnt, [1] sum rerank
-  unsigned int* stat_max;       // [0] max cnt, [1] max rerank
+  int* fail_list;
 };
 
 // fp64 distance of one base row to the query held in shared memory, computed by one warp.
@@ -388,13 +478,17 @@ __device__ __forceinline__ double warp_exact_distance(int metric, const float* s
 __global__ void __launch_bounds__(FIN_THREADS)
 finish_kernel(const FinParams p) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
-  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(fin_smem);            // [LOG_CAP]
-  double* s_key = reinterpret_cast<double*>(fin_smem + LOG_CAP * 8);                      // [RERANK_MAX]
-  long long* s_id = reinterpret_cast<long long*>(fin_smem + LOG_CAP * 8 + RERANK_MAX * 8);
-  float* s_q = reinterpret_cast<float*>(fin_smem + LOG_CAP * 8 + RERANK_MAX * 16);        // [d]
-  __shared__ double s_red[FIN_THREADS / 32];
+  // [LOG_CAP] packed (key, row) records; once sorted only the first R <= RERANK_MAX are needed,
+  // so the fp64 (distance, id) arrays of the re-rank live in the tail of the same buffer
+  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(fin_smem);
+  double* s_key = reinterpret_cast<double*>(fin_smem + RERANK_MAX * 8);
+  long long* s_id = reinterpret_cast<long long*>(fin_smem + RERANK_MAX * 8 + RERANK_MAX * 8);
+  float* s_q = reinterpret_cast<float*>(fin_smem + LOG_CAP * 8);                            // [d]
+  __shared__ double s_qn2;
+  __shared__ double s_eps;
   __shared__ int s_R;
   __shared__ int s_fail;
+  __shared__ float s_ratio[FIN_THREADS / 32];
 
   const long long q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,26 +505,36 @@ finish_kernel(const FinParams p) {
     double a = 0.0;
     for (int c2 = lane; c2 < p.d; c2 += 32) { double v = s_q[c2]; a = fma(v, v, a); }
     a = warp_sum(a);
-    if (lane == 0) s_red[0] = a;
+    if (lane == 0) s_qn2 = a;
   }
   __syncthreads();
-  const double qn2 = s_red[0];
+  const double qn2 = s_qn2;
 
   if (threadIdx.x == 0) {
     int fail = 0, R = 0;
+    double eps = 0.0;
     if (total > (unsigned int)LOG_CAP || c < p.k) {
       fail = 1;
     } else {
-      // proven bound on |tf32 key - exact key| for this query (see DESIGN.md "error bound")
+      // proven bound on |approximate key - exact key| for this query (DESIGN.md "error bound")
       const double qn = sqrt(qn2);
-      const double bnmax = sqrt((double)__uint_as_float(*p.bn2max));
-      double eps = (double)p.c_err * qn;
-      if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps *= 2.0 * bnmax;
-      else if (p.metric == NWK_METRIC_DOT) eps *= bnmax;
+      const double bnmax = sqrt((double)__uint_as_float(p.sc->bn2max));
+      double eps_dot = (double)p.c_rel * qn * bnmax;
+      double eps_cos = (double)p.c_rel * qn;
+      if (p.f16) {
+        // query elements below fp16's normal range after scaling are quantised to 2^-25
+        const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
+        const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
+        eps_dot += qquant * bnmax;
+        eps_cos += qquant;
+      }
+      eps = eps_dot;
+      if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
+      else if (p.metric == NWK_METRIC_COSINE) eps = eps_cos;
       const float key_k = ord2f((uint32_t)(s_log[p.k - 1] >> 32));
-      // inflate by the fp32 rounding of alpha + beta*acc itself
-      const float thr = __double2float_ru((double)key_k + 2.0 * eps * 1.0001 +
-                                          4.0e-7 * fabs((double)key_k) + 1e-30);
+      // + the fp32 rounding of alpha + beta*acc itself
+      eps += 3.0e-7 * fabs((double)key_k) + 1e-30;
+      const float thr = __double2float_ru((double)key_k + 2.0 * eps);
       const float tau = p.tau[q];
       if (!(thr < tau)) fail = 1;          // band reaches the logging threshold: cannot certify
       // R = number of logged keys <= thr (log is sorted)
@@ -445,12 +549,13 @@ finish_kernel(const FinParams p) {
     }
     s_fail = fail;
     s_R = R;
-    atomicAdd(p.stat_sum + 0, (unsigned long long)total);
-    atomicAdd(p.stat_sum + 1, (unsigned long long)R);
-    atomicMax(p.stat_max + 0, total);
-    atomicMax(p.stat_max + 1, (unsigned int)R);
+    s_eps = eps;
+    atomicAdd(p.sc->stat_sum + 0, (unsigned long long)total);
+    atomicAdd(p.sc->stat_sum + 1, (unsigned long long)R);
+    atomicMax(p.sc->stat_max + 0, total);
+    atomicMax(p.sc->stat_max + 1, (unsigned int)R);
     if (fail) {
-      int slot = atomicAdd(p.fail_cnt, 1);
+      int slot = atomicAdd(&p.sc->fail_cnt, 1);
       p.fail_list[slot] = (int)q;
     }
   }
@@ -459,21 +564,42 @@ finish_kernel(const FinParams p) {
   const int R = s_R;
   const int r2 = max(next_pow2(R), 2);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const double eps = s_eps;
+  // exact key = distance - key_shift (|q|^2 for sq-L2, 1 for cosine / dot)
+  const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
+  float ratio = 0.f;
 
-  for (int i = warp; i < r2; i += FIN_THREADS / 32) {
+  for (int i0 = 0; i0 < r2; i0 += FIN_THREADS / 32) {
+    const int i = i0 + warp;
+    long long row = -1;
+    float akey = 0.f;
     if (i < R) {
-      const long long row = (long long)(s_log[i] & 0xffffffffull);
-      double dist = warp_exact_distance(p.metric, s_q, p.base + row * p.d, p.d, qn2, lane);
-      if (lane == 0) { s_key[i] = (dist != dist) ? INF : dist; s_id[i] = row; }
-    } else if (lane == 0) {
-      s_key[i] = INF;
-      s_id[i] = 0x7fffffffffffffffLL;
+      const unsigned long long rec = s_log[i];
+      row = (long long)(rec & 0xffffffffull);
+      akey = ord2f((uint32_t)(rec >> 32));
+    }
+    double dist = INF;
+    if (row >= 0) {
+      dist = warp_exact_distance(p.metric, s_q, p.base + row * p.d, p.d, qn2, lane);
+      if (dist == dist) ratio = fmaxf(ratio, (float)(fabs((double)akey - (dist - key_shift)) / eps));
+      else dist = INF;
+    }
+    // s_key / s_id alias s_log[RERANK_MAX ..): disjoint from the R <= RERANK_MAX records read here
+    if (lane == 0 && i < r2) {
+      s_key[i] = dist;
+      s_id[i] = row >= 0 ? row : 0x7fffffffffffffffLL;
     }
   }
+  if (lane == 0) s_ratio[warp] = ratio;
   block_bitonic_sort(s_key, s_id, r2);
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
     p.out_dist[q * p.k + j] = (float)s_key[j];
     p.out_idx[q * p.k + j] = s_id[j] + p.id_offset;
+  }
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int w = 0; w < FIN_THREADS / 32; ++w) r = fmaxf(r, s_ratio[w]);
+    atomicMax(&p.sc->err_ratio, __float_as_uint(r));
   }
 }
 
@@ -499,16 +625,20 @@ static int get_encode_fn(EncodeTiledFn* out) {
   return NWK_OK;
 }
 
-static int make_tmap(CUtensorMap* tm, const float* ptr, long long rows, int d, int box_rows) {
+// 2-D row-major operand [rows, row_elems] (elements of 4 or 2 bytes); box = 128 bytes x box_rows
+static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long row_elems, bool f16,
+                     int box_rows) {
   EncodeTiledFn enc;
   NWK_TRY(get_encode_fn(&enc));
-  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)d * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const int esz = f16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(NWK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return NWK_OK;
 }
@@ -516,9 +646,12 @@ static int make_tmap(CUtensorMap* tm, const float* ptr, long long rows, int d, i
 static int tc_optin() {
   static bool done = false;
   if (!done) {
-    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     done = true;
   }
   return NWK_OK;
@@ -530,16 +663,19 @@ bool tc_path_supported(long long nb, long long nq, int d, int k) {
 }
 
 struct TcPlan {
-  int nQT, nT, nKB, G, nChunks, nUnits, nS, m, target;
+  int nQT, nT, nKB, G, nChunks, nUnits, nS, sChunks, dh;
   bool sample;
   long long nb_pad, nq_pad;
 };
 
-static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms) {
+static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16) {
+  (void)k;
   TcPlan pl{};
+  const int bk = f16 ? 64 : 32;
+  pl.dh = (d + 7) / 8 * 8;
   pl.nQT = (int)((nq + TQ - 1) / TQ);
   pl.nT = (int)((nb + TB - 1) / TB);
-  pl.nKB = (d + BK - 1) / BK;
+  pl.nKB = (d + bk - 1) / bk;
   pl.nb_pad = (long long)pl.nT * TB;
   pl.nq_pad = (long long)pl.nQT * TQ;
   long long pairs = (long long)pl.nQT * pl.nT;
@@ -547,61 +683,58 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms) {
   pl.G = (int)(g < 1 ? 1 : (g > 16 ? 16 : g));
   pl.nChunks = (pl.nT + pl.G - 1) / pl.G;
   pl.nUnits = pl.nChunks * pl.nQT;
-  pl.target = 3 * k + 256;
-  if (pl.target < 768) pl.target = 768;
-  // sampling only pays when the base is much larger than the population we aim to log
-  pl.sample = nb > 2ll * pl.target;
+  // sampling only pays when the base is larger than what the log can simply hold
+  pl.sample = nb > LOG_CAP / 2;
   if (pl.sample) {
-    long long want_rows = (24ll * nb + pl.target - 1) / pl.target;   // aims at m ~ 24
-    long long ns = (want_rows + TB - 1) / TB;
-    if (ns < 1) ns = 1;
+    // the SAMPLE_M-th smallest key of n_s sampled rows has about SAMPLE_M * nb / n_s rows of
+    // the whole base below it: n_s = SAMPLE_M * nb / LOG_TARGET
+    long long ns_rows = ((long long)SAMPLE_M * nb + LOG_TARGET - 1) / LOG_TARGET;
+    if (ns_rows < SAMPLE_M * 2) ns_rows = SAMPLE_M * 2;
+    long long cols;      // columns used per sample tile: spread small samples over >= 16 tiles
+    if (ns_rows >= 16 * TB) cols = TB;
+    else { cols = (ns_rows / 16 + 31) / 32 * 32; if (cols < 32) cols = 32; }
+    long long ns = (ns_rows + cols - 1) / cols;
     if (ns > pl.nT) ns = pl.nT;
+    if (ns < 1) ns = 1;
     pl.nS = (int)ns;
-    // rows actually covered by the sample tiles (the last base tile may be partial)
-    long long rows = 0;
-    for (int i = 0; i < pl.nS; ++i) {
-      long long t = ((long long)i * pl.nT) / pl.nS;
-      long long r = nb - t * TB;
-      rows += r < TB ? r : TB;
-    }
-    double mm = (double)pl.target * (double)rows / (double)nb;
-    int m = (int)(mm + 0.5);
-    if (m < 4) m = 4;
-    if (m > M_MAX) m = M_MAX;
-    pl.m = m;
+    pl.sChunks = (int)(cols / 32);
   }
   return pl;
 }
 
 size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
-  TcPlan pl = make_plan(nb, nq, d, k, 148);
+  TcPlan pl = make_plan(nb, nq, d, k, 148, true);
   size_t bytes = 0;
   bytes += align_up((size_t)pl.nb_pad * 4, 256) * 2;        // alpha, beta
   bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
   bytes += align_up((size_t)nq * 4, 256);                   // cnt
   bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
   bytes += align_up((size_t)nq * 4, 256);                   // fail list
+  bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
+  bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
   bytes += 4096;                                            // scalars
   // fallback scan for up to 64 queries is always provisioned; more is handled in rounds
   bytes += exact_scan_workspace_bytes(nb, 64, k) + 256;
   return bytes + 4096;
 }
 
-struct Scalars {            // one 256-byte block of device scalars, zeroed per call
-  unsigned int bn2max;
-  int err;
-  int fail_cnt;
-  unsigned int stat_max[2];
-  unsigned int pad;
-  unsigned long long stat_sum[2];
-};
+template <bool F16>
+static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMap& tb, const TcParams& p,
+                     cudaStream_t s) {
+  if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else tc_kernel<MODE_DUMP, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  NWK_LAUNCH_CHECK();
+  return NWK_OK;
+}
 
 int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
            unsigned int flags, nwk_knn_stats* stats, cudaStream_t s) {
   NWK_TRY(tc_optin());
   const int sms = sm_count();
-  TcPlan pl = make_plan(nb, nq, d, k, sms);
+  const bool f16 = !(flags & NWK_FLAG_TF32);
+  TcPlan pl = make_plan(nb, nq, d, k, sms, f16);
   Arena ar(ws, ws_bytes);
   float* alpha = ar.take<float>((size_t)pl.nb_pad);
   float* beta = ar.take<float>((size_t)pl.nb_pad);
@@ -609,6 +742,8 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   unsigned int* cnt = ar.take<unsigned int>((size_t)nq);
   unsigned long long* log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
   int* fail_list = ar.take<int>((size_t)nq);
+  __half* bh = ar.take<__half>((size_t)nb * pl.dh);
+  __half* qh = ar.take<__half>((size_t)nq * pl.dh);
   Scalars* sc = ar.take<Scalars>(1);
   ar.off = align_up(ar.off, 256);
   void* scan_ws = ar.base + ar.off;
@@ -625,28 +760,38 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
   NWK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, s));
 
+  if (f16) {
+    qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
+    NWK_LAUNCH_CHECK();
+    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
+    NWK_LAUNCH_CHECK();
+  }
   {
     long long blocks = (pl.nb_pad + 7) / 8;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-    rownorm_kernel<<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, metric, alpha, beta, &sc->bn2max);
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh);
     NWK_LAUNCH_CHECK();
   }
-
   if (profile) cudaEventRecord(ev[1], s);
+
   CUtensorMap tm_q, tm_b;
-  NWK_TRY(make_tmap(&tm_q, query, nq, d, TQ));
-  NWK_TRY(make_tmap(&tm_b, base, nb, d, TB));
+  if (f16) {
+    NWK_TRY(make_tmap(&tm_q, qh, nq, pl.dh, true, TQ));
+    NWK_TRY(make_tmap(&tm_b, bh, nb, pl.dh, true, TB));
+  } else {
+    NWK_TRY(make_tmap(&tm_q, query, nq, d, false, TQ));
+    NWK_TRY(make_tmap(&tm_b, base, nb, d, false, TB));
+  }
 
   TcParams p{};
-  p.d = d; p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
-  p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.m = pl.m;
+  p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
+  p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.cnt = cnt; p.log = log; p.err = &sc->err;
-
 
   if (pl.sample) {
     int grid = pl.nQT < sms ? pl.nQT : sms;
-    tc_kernel<MODE_SAMPLE><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    NWK_LAUNCH_CHECK();
+    NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_b, p, s));
   } else {
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
     NWK_LAUNCH_CHECK();
@@ -654,21 +799,22 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (profile) cudaEventRecord(ev[2], s);
   {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
-    tc_kernel<MODE_FILTER><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    NWK_LAUNCH_CHECK();
+    NWK_TRY(f16 ? launch_tc<true>(MODE_FILTER, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_FILTER, grid, tm_q, tm_b, p, s));
   }
   if (profile) cudaEventRecord(ev[3], s);
 
   FinParams f{};
   f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
-  f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.bn2max = &sc->bn2max;
-  // TF32 operands carry 11 significant bits (truncation error < 2^-10 each, product < 2^-9),
-  // accumulation over d terms in fp32 adds at most d * 2^-22 relative to sum |q_i b_i|.
-  f.c_err = (float)(1.0 / 512.0 * 1.001 + (double)d / 4194304.0);
-  f.out_dist = out_dist; f.out_idx = out_idx; f.fail_cnt = &sc->fail_cnt; f.fail_list = fail_list;
-  f.stat_sum = sc->stat_sum; f.stat_max = sc->stat_max;
+  f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
+  // Relative error of acc against sum |q_i b_i| <= |q||b|:
+  //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
+  //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
+  // plus the fp32 accumulation inside the tensor core, budgeted at 4 ulp per MMA step.
+  const double steps = (double)d / (f16 ? 16.0 : 8.0) + 2.0;
+  f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
+  f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   {
-    const int fin_smem = LOG_CAP * 8 + RERANK_MAX * 16 + d * 4 + 16;
+    const int fin_smem = LOG_CAP * 8 + d * 4 + 16;
     static int fin_optin = 0;
     if (fin_smem > fin_optin) {
       NWK_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem));
@@ -683,6 +829,10 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   NWK_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
   NWK_CUDA(cudaStreamSynchronize(s));
   if (h.err != 0) return fail(NWK_ERR_INTERNAL, "tcgen05 pipeline watchdog expired (role code %d)", h.err);
+  float err_ratio;
+  memcpy(&err_ratio, &h.err_ratio, 4);
+  if (err_ratio > 1.0f)
+    return fail(NWK_ERR_INTERNAL, "candidate keys exceeded the proven error bound (ratio %.3f)", err_ratio);
 
   if (h.fail_cnt > 0 && !(flags & NWK_FLAG_NO_FALLBACK)) {
     // uncertified queries: fp64 scan, in rounds that fit the provisioned scratch
@@ -700,15 +850,16 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (profile) cudaEventRecord(ev[5], s);
   NWK_CUDA(cudaStreamSynchronize(s));
   if (stats) {
-    stats->path = 1;
+    stats->path = f16 ? 1 : 2;
     stats->n_fallback_queries = h.fail_cnt;
     stats->max_candidates = (int)h.stat_max[0];
     stats->max_rerank = (int)h.stat_max[1];
     stats->total_candidates = (long long)h.stat_sum[0];
     stats->total_rerank = (long long)h.stat_sum[1];
     stats->gpu_launches = (int)(g_launches.load() - launches0);
+    stats->max_err_ratio = err_ratio;
     if (profile) {
-      cudaEventElapsedTime(&stats->ms_rownorm, ev[0], ev[1]);
+      cudaEventElapsedTime(&stats->ms_prep, ev[0], ev[1]);
       cudaEventElapsedTime(&stats->ms_sample, ev[1], ev[2]);
       cudaEventElapsedTime(&stats->ms_filter, ev[2], ev[3]);
       cudaEventElapsedTime(&stats->ms_finish, ev[3], ev[4]);
@@ -720,26 +871,64 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   return NWK_OK;
 }
 
+// MODE_DUMP writes raw accumulators; with fp16 operands acc = 2^(sq+sb_j) * dot, and the DOT
+// metric's beta_j is exactly -2^-(sq+sb_j), so out * (-beta_j) is the plain dot product.
+__global__ void dump_unscale_kernel(float* out, const float* beta, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < TQ * TB) out[i] = out[i] * (-beta[(long long)t * TB + (i % TB)]);
+}
+
 int tc_debug_tile(const float* base, long long nb, const float* query, long long nq, int d, long long b0,
-                  long long q0, float* out, cudaStream_t s) {
+                  long long q0, float* out, int use_f16, cudaStream_t s) {
   if (d % 4 != 0 || b0 % TB != 0 || q0 % TQ != 0) return fail(NWK_ERR_ARG, "debug tile: bad alignment");
   NWK_TRY(tc_optin());
+  const int sms = sm_count();
+  const bool f16 = use_f16 != 0;
+  TcPlan pl = make_plan(nb, nq, d, 1, sms, f16);
+  float *alpha = nullptr, *beta = nullptr;
+  __half *bh = nullptr, *qh = nullptr;
+  Scalars* sc = nullptr;
+  NWK_CUDA(cudaMalloc(&sc, sizeof(Scalars)));
+  NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
+  NWK_CUDA(cudaMalloc(&alpha, pl.nb_pad * 4));
+  NWK_CUDA(cudaMalloc(&beta, pl.nb_pad * 4));
   CUtensorMap tm_q, tm_b;
-  NWK_TRY(make_tmap(&tm_q, query, nq, d, TQ));
-  NWK_TRY(make_tmap(&tm_b, base, nb, d, TB));
-  int* err = nullptr;
-  NWK_CUDA(cudaMalloc(&err, 4));
-  NWK_CUDA(cudaMemsetAsync(err, 0, 4, s));
-  TcParams p{};
-  p.d = d; p.nKB = (d + BK - 1) / BK; p.nq = nq; p.nb = nb;
-  p.nQT = (int)((nq + TQ - 1) / TQ); p.nT = (int)((nb + TB - 1) / TB);
-  p.dump = out; p.dump_qt = (int)(q0 / TQ); p.dump_t = (int)(b0 / TB); p.err = err;
-  tc_kernel<MODE_DUMP><<<1, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-  NWK_LAUNCH_CHECK();
+  int rc = NWK_OK;
+  if (f16) {
+    NWK_CUDA(cudaMalloc(&bh, (size_t)nb * pl.dh * 2));
+    NWK_CUDA(cudaMalloc(&qh, (size_t)nq * pl.dh * 2));
+    qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
+    NWK_LAUNCH_CHECK();
+    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
+    NWK_LAUNCH_CHECK();
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh);
+    NWK_LAUNCH_CHECK();
+    rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
+    if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
+  } else {
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh);
+    NWK_LAUNCH_CHECK();
+    rc = make_tmap(&tm_q, query, nq, d, false, TQ);
+    if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);
+  }
   int h = 0;
-  NWK_CUDA(cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, s));
-  NWK_CUDA(cudaStreamSynchronize(s));
-  cudaFree(err);
+  if (rc == NWK_OK) {
+    TcParams p{};
+    p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
+    p.dump = out; p.dump_qt = (int)(q0 / TQ); p.dump_t = (int)(b0 / TB); p.err = &sc->err;
+    rc = f16 ? launch_tc<true>(MODE_DUMP, 1, tm_q, tm_b, p, s) : launch_tc<false>(MODE_DUMP, 1, tm_q, tm_b, p, s);
+    if (rc == NWK_OK) {
+      dump_unscale_kernel<<<(TQ * TB + 255) / 256, 256, 0, s>>>(out, beta, p.dump_t);
+      count_launch();
+      Scalars hs{};
+      cudaMemcpyAsync(&hs, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s);
+      cudaError_t e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = fail(NWK_ERR_CUDA, "debug tile failed: %s", cudaGetErrorString(e));
+      h = hs.err;
+    }
+  }
+  cudaFree(sc); cudaFree(alpha); cudaFree(beta); cudaFree(bh); cudaFree(qh);
+  if (rc != NWK_OK) return rc;
   if (h != 0) return fail(NWK_ERR_INTERNAL, "tcgen05 pipeline watchdog expired (role code %d)", h);
   return NWK_OK;
 }

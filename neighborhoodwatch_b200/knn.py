@@ -55,7 +55,7 @@ def _as_f32_cuda(x: torch.Tensor, name: str) -> torch.Tensor:
 
 def knn(dataset: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "sqeuclidean",
         id_offset: int = 0, force_exact_scan: bool = False, no_fallback: bool = False, profile: bool = False,
-        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        tf32: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exact k nearest neighbours; drop-in for brute_force.knn(dataset, queries, k)."""
     global last_stats
     lib = _native.load()
@@ -72,7 +72,7 @@ def knn(dataset: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "sqe
     nq = queries.shape[0]
     dev = dataset.device
     flags = ((_native.FLAG_FORCE_EXACT_SCAN if force_exact_scan else 0) | (_native.FLAG_NO_FALLBACK if no_fallback else 0)
-             | (_native.FLAG_PROFILE if profile else 0))
+             | (_native.FLAG_PROFILE if profile else 0) | (_native.FLAG_TF32 if tf32 else 0))
     with torch.cuda.device(dev):
         if out is None:
             out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -199,8 +199,8 @@ def knn_host(base, queries, k: int, metric: str = "sqeuclidean", id_offset: int 
     return out_d, out_i
 
 
-def debug_tc_tile(dataset: torch.Tensor, queries: torch.Tensor, b0: int, q0: int) -> torch.Tensor:
-    """Raw TF32 tensor-core dot products of one 128x256 tile pair (descriptor validation)."""
+def debug_tc_tile(dataset: torch.Tensor, queries: torch.Tensor, b0: int, q0: int, f16: bool = True) -> torch.Tensor:
+    """Raw tensor-core dot products of one 128x256 tile pair (descriptor validation)."""
     lib = _native.load()
     dataset = _as_f32_cuda(dataset, "dataset")
     queries = _as_f32_cuda(queries, "queries")
@@ -208,6 +208,6 @@ def debug_tc_tile(dataset: torch.Tensor, queries: torch.Tensor, b0: int, q0: int
     with torch.cuda.device(dev):
         out = torch.zeros((128, 256), dtype=torch.float32, device=dev)
         rc = lib.nwk_debug_tc_tile(dataset.data_ptr(), dataset.shape[0], queries.data_ptr(), queries.shape[0],
-                                   dataset.shape[1], b0, q0, out.data_ptr(), _stream_ptr(dev))
+                                   dataset.shape[1], b0, q0, out.data_ptr(), 1 if f16 else 0, _stream_ptr(dev))
         _native.check(rc)
     return out

@@ -47,22 +47,48 @@ def test_exact_scan_parity(cuda_device, metric, nq, nb, d, k):
     assert res["index_mismatches_tied"] == 0      # the fp64 scan has the oracle's arithmetic
 
 
-def test_tc_tile_matches_tf32_model(cuda_device):
-    """Validates TMA map, UMMA descriptors and TMEM read-back in isolation."""
+@pytest.mark.parametrize("f16", [True, False], ids=["fp16", "tf32"])
+def test_tc_tile_matches_operand_model(cuda_device, f16):
+    """Validates TMA map, UMMA descriptors and TMEM read-back in isolation, and the error
+    constant the certification relies on."""
     from neighborhoodwatch_b200 import knn
     rng = np.random.default_rng(0)
-    for d in (32, 64, 384, 100):
-        base = rng.standard_normal((600, d)).astype(np.float32)
+    worst = 0.0
+    for d in (32, 64, 384, 100, 1536):
+        base = (rng.standard_normal((600, d)) * rng.uniform(0.01, 100.0, (600, 1))).astype(np.float32)
         q = rng.standard_normal((300, d)).astype(np.float32)
-        out = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 256, 128).cpu().numpy()
+        out = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 256, 128, f16=f16).cpu().numpy()
         exact = q[128:256].astype(np.float64) @ base[256:512].astype(np.float64).T
         scale = np.abs(q[128:256].astype(np.float64)) @ np.abs(base[256:512].astype(np.float64)).T
         err = np.abs(out - exact)
-        c = 2.0 ** -9 * 1.001 + d / 2.0 ** 22
-        assert np.all(err <= c * scale + 1e-6), f"d={d}: max err ratio {(err / (c * scale + 1e-6)).max()}"
+        if f16:
+            c = 2.0 ** -10 * 1.001 + (d / 16 + 2) / 2.0 ** 22
+        else:
+            c = 2.0 ** -9 * 1.001 + (d / 8 + 2) / 2.0 ** 22
+        ratio = (err / (c * scale + 1e-30)).max()
+        worst = max(worst, ratio)
+        assert ratio <= 1.0, f"d={d}: max err ratio {ratio}"
         # rows beyond the inputs read as zero (TMA out-of-bounds fill)
-        out2 = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 512, 256).cpu().numpy()
+        out2 = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 512, 256, f16=f16).cpu().numpy()
         assert np.all(out2[300 - 256:] == 0) and np.all(out2[:, 600 - 512:] == 0)
+    print("worst error / bound:", worst)
+
+
+def test_tc_operand_rounding_probe(cuda_device):
+    """Documents how the tensor core treats fp32 operands under kind::tf32 (truncate vs round)."""
+    from neighborhoodwatch_b200 import knn
+    base = np.zeros((256, 32), dtype=np.float32)
+    q = np.zeros((128, 32), dtype=np.float32)
+    base[:, 0] = 1.0
+    vals = [1 + 2.0 ** -11 + 2.0 ** -12, 1 + 2.0 ** -11, 1 + 2.0 ** -10 + 2.0 ** -11, 1 + 2.0 ** -12]
+    for i, v in enumerate(vals):
+        q[i, 0] = v
+    out = knn.debug_tc_tile(_dev(base, cuda_device), _dev(q, cuda_device), 0, 0, f16=False).cpu().numpy()
+    got = [float(out[i, 0]) for i in range(len(vals))]
+    trunc = [1.0, 1.0, 1 + 2.0 ** -10, 1.0]
+    rne = [1 + 2.0 ** -10, 1.0, 1 + 2.0 ** -9, 1.0]
+    print("tf32 operand probe:", got, "truncation" if got == trunc else ("round-nearest-even" if got == rne else "other"))
+    assert all(abs(g - v) <= 2.0 ** -10 * 1.001 for g, v in zip(got, vals))
 
 
 @pytest.mark.parametrize("metric", ko.METRICS)
@@ -82,7 +108,20 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     assert st["path"] == 1, st
     res = _check(got_d, got_i, base, q, k, metric, id_offset=5)
     assert st["n_fallback_queries"] <= max(1, nq // 100), st
+    assert 0.0 < st["max_err_ratio"] <= 1.0, st
     print(metric, (nq, nb, d, k), st, res)
+
+
+@pytest.mark.parametrize("metric", ko.METRICS)
+def test_tc_knn_parity_tf32_operands(cuda_device, metric):
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(20000, 256, 1234)
+    q = synth.vectors(300, 256, 5678)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric=metric, tf32=True)
+    st = dict(knn.last_stats)
+    assert st["path"] == 2 and st["max_err_ratio"] <= 1.0, st
+    _check(got_d, got_i, base, q, 100, metric)
+    print(metric, st)
 
 
 def test_tc_gaussian_unnormalised(cuda_device):
