@@ -55,11 +55,14 @@ constexpr int TC_THREADS = 256;
 constexpr int STAGE_A_BYTES = TQ * 128;        // 16 KB: 128 rows x one 128-byte swizzle span
 constexpr int STAGE_B_BYTES = TB * 128;        // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int AB_BYTES = ACC_STAGES * 2 * TB * 4;        // alpha + beta of the tile in each accumulator stage
+constexpr int APPEND_SLOTS = 8;                          // per-thread staging of candidate records
+constexpr int APPEND_BYTES = APPEND_SLOTS * TQ * 8;
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + 256 + 1024;
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
-constexpr int LOG_CAP = 8192;                  // candidate-log slots per query
-constexpr int LOG_TARGET = 1536;               // population the sampled threshold aims at
-constexpr int RERANK_MAX = 2048;               // most rows re-ranked in fp64 per query
+constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
+constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
+constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
 constexpr int TC_MAX_K = 256;
 constexpr int FIN_THREADS = 256;
 
@@ -255,12 +258,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   // 1024-byte alignment for the 128B-swizzled operand tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* s_ab = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [ACC_STAGES][2][TB]
+  unsigned long long* s_app = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES + AB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* abfull_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [ACC_STAGES]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3 * ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,7 +277,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&abfull_bar[a], 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -313,6 +323,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       while (ok && sch.next(qt, t, first, last)) {
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
         ptx::tc_fence_after();
+        if (MODE != MODE_DUMP) {
+          // the epilogue has released this stage: refill its alpha / beta tile (2 x 1 KB)
+          float* ab = s_ab + acc * 2 * TB;
+          ptx::mbar_arrive_expect_tx(&abfull_bar[acc], 2 * TB * 4);
+          ptx::bulk_load_1d(ab, p.alpha + (long long)t * TB, TB * 4, &abfull_bar[acc]);
+          ptx::bulk_load_1d(ab + TB, p.beta + (long long)t * TB, TB * 4, &abfull_bar[acc]);
+        }
         const uint32_t d_tmem = tmem_base + acc * TB;
         for (int kb = 0; kb < p.nKB; ++kb) {
           if (!ptx::mbar_wait(&full_bar[stage], phase, p.err, ERR_MMA_FULL)) { ok = false; break; }
@@ -345,6 +362,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     float tau = -INF;
     long long q = 0;
     float lst[SAMPLE_M];      // SAMPLE: ascending list of the smallest keys seen (registers)
+    int nst = 0;              // FILTER: records staged in this thread's shared-memory slots
     bool ok = true;
     while (ok && sch.next(qt, t, first, last)) {
       if (first) {
@@ -357,11 +375,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           for (int j = 0; j < SAMPLE_M; ++j) lst[j] = INF;
         }
       }
+      if (MODE != MODE_DUMP) {
+        if (!ptx::mbar_wait(&abfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
+      }
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
-      const float4* al4 = reinterpret_cast<const float4*>(p.alpha + (long long)t * TB);
-      const float4* be4 = reinterpret_cast<const float4*>(p.beta + (long long)t * TB);
+      const float4* al4 = reinterpret_cast<const float4*>(s_ab + acc * 2 * TB);
+      const float4* be4 = reinterpret_cast<const float4*>(s_ab + acc * 2 * TB + TB);
       const long long row0 = (long long)t * TB;
       const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : TB / 32;
 
@@ -381,8 +402,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         } else {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 al = __ldg(al4 + ch * 8 + j4);
-            const float4 be = __ldg(be4 + ch * 8 + j4);
+            const float4 al = al4[ch * 8 + j4];           // shared-memory broadcast reads
+            const float4 be = be4[ch * 8 + j4];
             float k0 = fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x);
             float k1 = fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y);
             float k2 = fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z);
@@ -392,26 +413,28 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float key = kk[e];
-                if (MODE == MODE_FILTER) {
-                  if (key < tau) {
-                    const unsigned int slot = atomicAdd(p.cnt + q, 1u);
-                    if (slot < LOG_CAP) {
-                      const unsigned long long rec =
-                          (static_cast<unsigned long long>(f2ord(key)) << 32) |
-                          static_cast<unsigned long long>(row0 + ch * 32 + j4 * 4 + e);
-                      p.log[q * LOG_CAP + slot] = rec;
-                    }
-                  }
-                } else {
-                  // branch-free insertion: bubble the key through the sorted register list
-                  float kx = (key < tau) ? key : INF;
+                if (key < tau) {
+                  if (MODE == MODE_FILTER) {
+                    // stage the record in this thread's private shared-memory slots; one global
+                    // atomic reserves log space for a whole batch when the slots are full
+                    s_app[nst * TQ + row_in_tile] =
+                        (static_cast<unsigned long long>(f2ord(key)) << 32) |
+                        static_cast<unsigned long long>(row0 + ch * 32 + j4 * 4 + e);
+                    if (++nst == APPEND_SLOTS) {
+                      const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
 #pragma unroll
-                  for (int j = 0; j < SAMPLE_M; ++j) {
-                    const float lo = fminf(lst[j], kx);
-                    kx = fmaxf(lst[j], kx);
-                    lst[j] = lo;
+                      for (int j = 0; j < APPEND_SLOTS; ++j)
+                        if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * TQ + row_in_tile];
+                      nst = 0;
+                    }
+                  } else {
+                    // insert into the ascending register list and drop the largest:
+                    // new[j] = max(old[j-1], min(old[j], key)) -- every slot independent
+#pragma unroll
+                    for (int j = SAMPLE_M - 1; j > 0; --j) lst[j] = fmaxf(lst[j - 1], fminf(lst[j], key));
+                    lst[0] = fminf(lst[0], key);
+                    tau = lst[SAMPLE_M - 1];
                   }
-                  tau = (q < p.nq) ? lst[SAMPLE_M - 1] : -INF;
                 }
               }
             }
@@ -423,6 +446,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       if (MODE == MODE_SAMPLE && last && q < p.nq) p.tau[q] = tau;
+      if (MODE == MODE_FILTER && last && nst > 0) {
+        const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)nst);
+        for (int j = 0; j < nst; ++j)
+          if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * TQ + row_in_tile];
+        nst = 0;
+      }
     }
   }
 
@@ -565,29 +594,65 @@ finish_kernel(const FinParams p) {
   const int r2 = max(next_pow2(R), 2);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const double eps = s_eps;
-  // exact key = distance - key_shift (|q|^2 for sq-L2, 1 for cosine / dot)
+  // exact key = (distance - key_shift) * key_scale: the candidate keys omit the per-query
+  // constants (|q|^2 for sq-L2, the 1 of cosine / dot, and cosine's 1/|q|)
   const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
+  const double key_scale = (p.metric == NWK_METRIC_COSINE) ? sqrt(qn2) : 1.0;
   float ratio = 0.f;
 
-  for (int i0 = 0; i0 < r2; i0 += FIN_THREADS / 32) {
-    const int i = i0 + warp;
-    long long row = -1;
-    float akey = 0.f;
-    if (i < R) {
-      const unsigned long long rec = s_log[i];
-      row = (long long)(rec & 0xffffffffull);
-      akey = ord2f((uint32_t)(rec >> 32));
+  // each warp keeps FIN_ROWS candidate rows in flight (independent loads) per iteration
+  constexpr int FIN_ROWS = 4;
+  for (int i0 = warp * FIN_ROWS; i0 < r2; i0 += (FIN_THREADS / 32) * FIN_ROWS) {
+    long long rows[FIN_ROWS];
+    float akey[FIN_ROWS];
+    double acc[FIN_ROWS], bn2[FIN_ROWS];
+#pragma unroll
+    for (int r = 0; r < FIN_ROWS; ++r) {
+      rows[r] = -1; akey[r] = 0.f; acc[r] = 0.0; bn2[r] = 0.0;
+      if (i0 + r < R) {
+        const unsigned long long rec = s_log[i0 + r];
+        rows[r] = (long long)(rec & 0xffffffffull);
+        akey[r] = ord2f((uint32_t)(rec >> 32));
+      }
     }
-    double dist = INF;
-    if (row >= 0) {
-      dist = warp_exact_distance(p.metric, s_q, p.base + row * p.d, p.d, qn2, lane);
-      if (dist == dist) ratio = fmaxf(ratio, (float)(fabs((double)akey - (dist - key_shift)) / eps));
+    for (int c2 = lane * 4; c2 < p.d; c2 += 128) {
+      const float4 q4 = *reinterpret_cast<const float4*>(s_q + c2);
+      float4 b4[FIN_ROWS];
+#pragma unroll
+      for (int r = 0; r < FIN_ROWS; ++r)
+        b4[r] = rows[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.base + rows[r] * p.d + c2))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < FIN_ROWS; ++r) {
+        // same operation order as warp_exact_distance / scan_dist_kernel
+        const double b0 = b4[r].x, b1 = b4[r].y, b2 = b4[r].z, b3 = b4[r].w;
+        if (p.metric == NWK_METRIC_COSINE) {
+          bn2[r] = fma(b0, b0, bn2[r]); bn2[r] = fma(b1, b1, bn2[r]);
+          bn2[r] = fma(b2, b2, bn2[r]); bn2[r] = fma(b3, b3, bn2[r]);
+        }
+        if (p.metric == NWK_METRIC_SQEUCLIDEAN) {
+          const double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
+          acc[r] = fma(e0, e0, acc[r]); acc[r] = fma(e1, e1, acc[r]);
+          acc[r] = fma(e2, e2, acc[r]); acc[r] = fma(e3, e3, acc[r]);
+        } else {
+          acc[r] = fma((double)q4.x, b0, acc[r]); acc[r] = fma((double)q4.y, b1, acc[r]);
+          acc[r] = fma((double)q4.z, b2, acc[r]); acc[r] = fma((double)q4.w, b3, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < FIN_ROWS; ++r) {
+      double dist = warp_sum(acc[r]);
+      if (p.metric == NWK_METRIC_COSINE) bn2[r] = warp_sum(bn2[r]);
+      if (p.metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(p.metric, dist, qn2, bn2[r]);
+      if (rows[r] < 0) dist = INF;
+      else if (dist == dist) ratio = fmaxf(ratio, (float)(fabs((double)akey[r] - (dist - key_shift) * key_scale) / eps));
       else dist = INF;
-    }
-    // s_key / s_id alias s_log[RERANK_MAX ..): disjoint from the R <= RERANK_MAX records read here
-    if (lane == 0 && i < r2) {
-      s_key[i] = dist;
-      s_id[i] = row >= 0 ? row : 0x7fffffffffffffffLL;
+      // s_key / s_id alias s_log[RERANK_MAX ..): disjoint from the R <= RERANK_MAX records read above
+      if (lane == 0 && i0 + r < r2) {
+        s_key[i0 + r] = dist;
+        s_id[i0 + r] = rows[r] >= 0 ? rows[r] : 0x7fffffffffffffffLL;
+      }
     }
   }
   if (lane == 0) s_ratio[warp] = ratio;
