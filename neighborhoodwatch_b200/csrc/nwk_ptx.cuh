@@ -181,6 +181,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 
+// one column of the warp's 32 lanes
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+
 // K-major operand tile staged by TMA with 128-byte swizzle: rows of 128 B, 8-row groups
 // 1024 B apart.  (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).)

@@ -58,7 +58,8 @@ constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
 constexpr int AB_BYTES = ACC_STAGES * 2 * TB * 4;        // alpha + beta of the tile in each accumulator stage
 constexpr int APPEND_SLOTS = 8;                          // per-thread staging of candidate records
 constexpr int APPEND_BYTES = APPEND_SLOTS * TQ * 8;
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + 256 + 1024;
+constexpr int MASK_BYTES = (TB / 32) * TQ * 4;           // per-thread hit masks of the 8 column chunks
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES + 256 + 1024;
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
@@ -256,11 +257,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   constexpr int UMMA_K = Op<F16>::UMMA_K;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // (offset arithmetic on the __shared__ pointer keeps its address space: LDS/STS, not generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_ab = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [ACC_STAGES][2][TB]
   unsigned long long* s_app = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES + AB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
@@ -381,16 +383,23 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
-      const float4* al4 = reinterpret_cast<const float4*>(s_ab + acc * 2 * TB);
-      const float4* be4 = reinterpret_cast<const float4*>(s_ab + acc * 2 * TB + TB);
+      const float* s_al = s_ab + acc * 2 * TB;
+      const float* s_be = s_al + TB;
+      const float4* al4 = reinterpret_cast<const float4*>(s_al);
+      const float4* be4 = reinterpret_cast<const float4*>(s_be);
       const long long row0 = (long long)t * TB;
       const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : TB / 32;
 
+      // ---- fast path: one FFMA + compare per element, hits only recorded as bit masks ----
+      // (the unrolled body stays small enough for the instruction cache; everything rare is
+      //  in the single slow loop below, which re-reads the hit columns from TMEM)
       uint32_t va[32], vb[32];
+      uint32_t hit[TB / 32];
       ptx::tmem_ld_32x32(taddr, va);
 #pragma unroll
       for (int ch = 0; ch < TB / 32; ++ch) {
-        if (MODE == MODE_SAMPLE && ch >= nch) break;      // warp-uniform
+        hit[ch] = 0;
+        if (MODE == MODE_SAMPLE && ch >= nch) continue;   // warp-uniform
         ptx::tmem_wait_ld();
         uint32_t(&cur)[32] = (ch & 1) ? vb : va;
         uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
@@ -400,41 +409,61 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j)
             p.dump[(long long)row_in_tile * TB + ch * 32 + j] = __uint_as_float(cur[j]);
         } else {
+          uint32_t mask = 0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 al = al4[ch * 8 + j4];           // shared-memory broadcast reads
             const float4 be = be4[ch * 8 + j4];
-            float k0 = fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x);
-            float k1 = fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y);
-            float k2 = fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z);
-            float k3 = fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w);
-            if ((k0 < tau) | (k1 < tau) | (k2 < tau) | (k3 < tau)) {
-              float kk[4] = {k0, k1, k2, k3};
+            if (fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x) < tau) mask |= 1u << (4 * j4 + 0);
+            if (fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y) < tau) mask |= 1u << (4 * j4 + 1);
+            if (fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z) < tau) mask |= 1u << (4 * j4 + 2);
+            if (fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w) < tau) mask |= 1u << (4 * j4 + 3);
+          }
+          hit[ch] = mask;
+        }
+      }
+      ptx::tmem_wait_ld();
+
+      // ---- slow path (rare): columns where some lane of the warp has a hit ----
+      if (MODE != MODE_DUMP) {
+        uint32_t anyhit = 0;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float key = kk[e];
-                if (key < tau) {
-                  if (MODE == MODE_FILTER) {
-                    // stage the record in this thread's private shared-memory slots; one global
-                    // atomic reserves log space for a whole batch when the slots are full
-                    s_app[nst * TQ + row_in_tile] =
-                        (static_cast<unsigned long long>(f2ord(key)) << 32) |
-                        static_cast<unsigned long long>(row0 + ch * 32 + j4 * 4 + e);
-                    if (++nst == APPEND_SLOTS) {
-                      const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
+        for (int ch = 0; ch < TB / 32; ++ch) anyhit |= hit[ch];
+        if (__any_sync(0xffffffffu, anyhit != 0)) {
 #pragma unroll
-                      for (int j = 0; j < APPEND_SLOTS; ++j)
-                        if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * TQ + row_in_tile];
-                      nst = 0;
-                    }
-                  } else {
-                    // insert into the ascending register list and drop the largest:
-                    // new[j] = max(old[j-1], min(old[j], key)) -- every slot independent
+          for (int ch = 0; ch < TB / 32; ++ch) s_mask[ch * TQ + row_in_tile] = hit[ch];   // thread-private slots
+#pragma unroll 1
+          for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t mine = s_mask[ch * TQ + row_in_tile];
+            uint32_t um = __reduce_or_sync(0xffffffffu, mine);
+            while (um) {
+              const int j = __ffs(um) - 1;
+              um &= um - 1;
+              const int col = ch * 32 + j;
+              const uint32_t v = ptx::tmem_ld_32x1(taddr + col);
+              ptx::tmem_wait_ld();
+              const float key = fmaf(s_be[col], __uint_as_float(v), s_al[col]);   // bit-identical to the fast path
+              if (((mine >> j) & 1u) && key < tau) {
+                if (MODE == MODE_FILTER) {
+                  // stage the record in this thread's private shared-memory slots; one global
+                  // atomic reserves log space for a whole batch when the slots are full
+                  s_app[nst * TQ + row_in_tile] =
+                      (static_cast<unsigned long long>(f2ord(key)) << 32) |
+                      static_cast<unsigned long long>(row0 + col);
+                  if (++nst == APPEND_SLOTS) {
+                    const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
 #pragma unroll
-                    for (int j = SAMPLE_M - 1; j > 0; --j) lst[j] = fmaxf(lst[j - 1], fminf(lst[j], key));
-                    lst[0] = fminf(lst[0], key);
-                    tau = lst[SAMPLE_M - 1];
+                    for (int i = 0; i < APPEND_SLOTS; ++i)
+                      if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * TQ + row_in_tile];
+                    nst = 0;
                   }
+                } else {
+                  // insert into the ascending register list and drop the largest:
+                  // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
+#pragma unroll
+                  for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
+                  lst[0] = fminf(lst[0], key);
+                  tau = lst[SAMPLE_M - 1];
                 }
               }
             }
