@@ -15,11 +15,12 @@
 //                    tau_q straight out of TMEM and appends the (rare) survivors to a
 //                    per-query candidate log.  The distance matrix never reaches HBM.
 //                    Tensor-pipe / L2 bound: 2*Q*B*d FLOP.
-//   finish_kernel    per query: sort the log, take every candidate whose approximate key lies
-//                    within 2*eps of the k-th (eps = proven error bound of the fp16 operands),
-//                    recompute those in fp64 from the fp32 inputs, order by (distance, index),
-//                    emit k.  A query is *certified* when tau_q lies above that band (no row
-//                    outside the log can belong to the true top-k); the rest go to the fp64 scan.
+//   select_kernel    per query: sort the log, keep every candidate whose approximate key lies
+//                    within 2*eps of the k-th (eps = proven error bound of the fp16 operands).
+//                    A query is *certified* when tau_q lies above that band (no row outside the
+//                    log can belong to the true top-k); the rest go to the fp64 scan.
+//   rerank_kernel    recompute the kept rows in fp64 from the fp32 inputs (HBM gather bound).
+//   output_kernel    order by (fp64 distance, index), emit k, check the error bound held.
 //
 // Operand precision: fp16 has the 11-bit significand of TF32; with exact power-of-two scaling
 // (per base row, global for the queries) every element is a normal fp16 number, so the
@@ -51,21 +52,21 @@ constexpr int TQ = 128;
 constexpr int TB = 256;
 constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;                // 4 control warps + 2 epilogue warpgroups
+constexpr int EPI_WG_MAX = 2;
 constexpr int STAGE_A_BYTES = TQ * 128;        // 16 KB: 128 rows x one 128-byte swizzle span
 constexpr int STAGE_B_BYTES = TB * 128;        // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
 constexpr int AB_BYTES = ACC_STAGES * 2 * TB * 4;        // alpha + beta of the tile in each accumulator stage
 constexpr int APPEND_SLOTS = 8;                          // per-thread staging of candidate records
-constexpr int APPEND_BYTES = APPEND_SLOTS * TQ * 8;
-constexpr int MASK_BYTES = (TB / 32) * TQ * 4;           // per-thread hit masks of the 8 column chunks
+constexpr int APPEND_BYTES = APPEND_SLOTS * TQ * EPI_WG_MAX * 8;
+constexpr int MASK_BYTES = (TB / 32) * TQ * 4;           // per-thread hit masks of its column chunks
 constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES + 256 + 1024;
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
 constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
 constexpr int TC_MAX_K = 256;
-constexpr int FIN_THREADS = 256;
 
 enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
 enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
@@ -85,6 +86,7 @@ struct TcParams {
   const float* alpha;       // [nT*TB]
   const float* beta;        // [nT*TB]
   float* tau;               // [nQT*TQ]
+  float* slist;             // SAMPLE: [nq][2][SAMPLE_M] smallest keys per query and sample half
   unsigned int* cnt;        // [nq]
   unsigned long long* log;  // [nq][LOG_CAP]
   float* dump;              // MODE_DUMP: [TQ][TB]
@@ -123,9 +125,12 @@ __device__ __forceinline__ int f16_scale_exp(float maxabs) {
   if (!(maxabs > 0.f)) return 0;
   int e;
   frexpf(maxabs, &e);       // maxabs = m * 2^e, m in [0.5, 1)
-  return 15 - e;
+  // clamped so that the combined query+row scale stays a normal fp32 power of two; data whose
+  // magnitudes lie outside 2^+-75 would leave fp16's range and is caught by the error monitor
+  return max(-60, min(60, 15 - e));
 }
 
+__device__ __forceinline__ float pow2f(int e);
 __global__ void __launch_bounds__(256)
 qprep_kernel(const float* __restrict__ q, long long nq, int d, int dh, const Scalars* __restrict__ sc,
              __half* __restrict__ qh) {
@@ -135,16 +140,25 @@ qprep_kernel(const float* __restrict__ q, long long nq, int d, int dh, const Sca
     long long r = i / dh;
     int c = (int)(i - r * dh);
     float v = c < d ? q[r * d + c] : 0.f;
-    qh[i] = __float2half_rn(ldexpf(v, s));
+    qh[i] = __float2half_rn(v * pow2f(s));
   }
 }
 
-// one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale
+// exact 2^e as a float (e in [-126, 127])
+__device__ __forceinline__ float pow2f(int e) {
+  e = max(-126, min(127, e));
+  return __int_as_float((e + 127) << 23);
+}
+
+// one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale.
+// The row is read once: up to ROW_CACHE float4 per lane stay in registers between the
+// norm / max pass and the conversion pass (d <= 1024); longer rows re-read their tail (L1/L2).
 template <bool F16>
 __global__ void __launch_bounds__(256)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
                 __half* __restrict__ bh) {
+  constexpr int ROW_CACHE = 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float INF = __int_as_float(0x7f800000);
   const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
@@ -155,10 +169,25 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       continue;
     }
     const float* brow = base + row * d;
+    float4 cache[ROW_CACHE];
+#pragma unroll
+    for (int i = 0; i < ROW_CACHE; ++i) {
+      const int c = lane * 4 + i * 128;
+      cache[i] = c < d ? __ldg(reinterpret_cast<const float4*>(brow + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     double a = 0.0;
     float mx = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(brow + c));
+#pragma unroll
+    for (int i = 0; i < ROW_CACHE; ++i) {
+      const float4 v = cache[i];
+      a = fma((double)v.x, (double)v.x, a);
+      a = fma((double)v.y, (double)v.y, a);
+      a = fma((double)v.z, (double)v.z, a);
+      a = fma((double)v.w, (double)v.w, a);
+      mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(mx, fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (int c = lane * 4 + ROW_CACHE * 128; c < d; c += 128) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(brow + c));
       a = fma((double)v.x, (double)v.x, a);
       a = fma((double)v.y, (double)v.y, a);
       a = fma((double)v.z, (double)v.z, a);
@@ -172,21 +201,35 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (!(mx < INF)) mx = 0.f;             // inf / nan rows: leave unscaled (they never rank)
       sb = f16_scale_exp(mx);
+      const float scale = pow2f(sb);         // exact power of two: v * scale is exact up to fp16 rounding
       __half* hrow = bh + row * dh;
-      for (int c = lane * 4; c < dh; c += 128) {
+#pragma unroll
+      for (int i = 0; i < ROW_CACHE; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < dh) {                        // dh % 8 == 0; columns in [d, dh) are zero
+          const float4 v = cache[i];
+          __half2 h01 = __floats2half2_rn(v.x * scale, v.y * scale);
+          __half2 h23 = __floats2half2_rn(v.z * scale, v.w * scale);
+          uint2 pk;
+          pk.x = *reinterpret_cast<unsigned int*>(&h01);
+          pk.y = *reinterpret_cast<unsigned int*>(&h23);
+          *reinterpret_cast<uint2*>(hrow + c) = pk;
+        }
+      }
+      for (int c = lane * 4 + ROW_CACHE * 128; c < dh; c += 128) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < d) v = __ldg(reinterpret_cast<const float4*>(brow + c));     // d % 4 == 0
-        __half2 h01 = __floats2half2_rn(ldexpf(v.x, sb), ldexpf(v.y, sb));
-        __half2 h23 = __floats2half2_rn(ldexpf(v.z, sb), ldexpf(v.w, sb));
+        if (c < d) v = __ldg(reinterpret_cast<const float4*>(brow + c));
+        __half2 h01 = __floats2half2_rn(v.x * scale, v.y * scale);
+        __half2 h23 = __floats2half2_rn(v.z * scale, v.w * scale);
         uint2 pk;
         pk.x = *reinterpret_cast<unsigned int*>(&h01);
         pk.y = *reinterpret_cast<unsigned int*>(&h23);
-        *reinterpret_cast<uint2*>(hrow + c) = pk;                            // dh % 8 == 0
+        *reinterpret_cast<uint2*>(hrow + c) = pk;
       }
     }
     if (lane == 0) {
       // acc = 2^(sq+sb) * (q.b) up to operand rounding: fold the scale into beta (exact)
-      const float unscale = ldexpf(1.f, -(sq + sb));
+      const float unscale = pow2f(-(sq + sb));
       float al = 0.f, be = -unscale;
       if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f * unscale; }
       else if (metric == NWK_METRIC_COSINE) {
@@ -198,6 +241,28 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     }
   }
   if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
+}
+
+// tau_q = SAMPLE_M-th smallest of the two half-sample lists of query q (one warp per query)
+__global__ void __launch_bounds__(256)
+tau_merge_kernel(const float* __restrict__ slist, long long nq, float* __restrict__ tau) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 8 + warp;
+  if (q >= nq) return;
+  // both lists are ascending: merge-path by rank.  Element a[i] of list A has rank
+  // i + #(b < a[i]) (+ ties broken towards A); the element with rank SAMPLE_M-1 is the answer.
+  const float a = slist[(q * 2 + 0) * SAMPLE_M + lane];
+  const float b = slist[(q * 2 + 1) * SAMPLE_M + lane];
+  int ra = lane, rb = lane;
+#pragma unroll
+  for (int j = 0; j < SAMPLE_M; ++j) {
+    const float bj = __shfl_sync(0xffffffffu, b, j);
+    const float aj = __shfl_sync(0xffffffffu, a, j);
+    ra += (bj < a) ? 1 : 0;
+    rb += (aj <= b) ? 1 : 0;
+  }
+  if (ra == SAMPLE_M - 1) tau[q] = a;
+  if (rb == SAMPLE_M - 1) tau[q] = b;
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -221,17 +286,24 @@ struct Sched {
   // advance to the next pair; returns false when the CTA is done
   __device__ __forceinline__ bool next(int& out_qt, int& out_t, bool& first, bool& last) {
     if (i >= len) {
-      u += gridDim.x;
       if (MODE == MODE_FILTER) {
+        u += gridDim.x;
         if (u >= nUnits) return false;
         c = u / nQT;
         qt = u - c * nQT;
         len = min(G, nT - c * G);
       } else if (MODE == MODE_SAMPLE) {
-        if (u >= nQT) return false;
-        qt = u;
-        len = nS;
+        // unit = (query tile, half of the sample tiles): 2*nQT units keep every SM busy;
+        // an empty half (nS == 1) is skipped, its list stays at the +inf it was filled with
+        do {
+          u += gridDim.x;
+          if (u >= 2 * nQT) return false;
+          qt = u >> 1;
+          c = (u & 1) ? (nS + 1) / 2 : 0;
+          len = (u & 1) ? nS - c : (nS + 1) / 2;
+        } while (len == 0);
       } else {
+        u += gridDim.x;
         if (u >= 1) return false;
         qt = dump_qt;
         len = 1;
@@ -240,7 +312,7 @@ struct Sched {
     }
     out_qt = qt;
     if (MODE == MODE_FILTER) out_t = c * G + i;
-    else if (MODE == MODE_SAMPLE) out_t = (int)(((long long)i * nT) / nS);
+    else if (MODE == MODE_SAMPLE) out_t = (int)(((long long)(c + i) * nT) / nS);
     else out_t = dump_t;
     first = (i == 0);
     last = (i == len - 1);
@@ -255,6 +327,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           const TcParams p) {
   constexpr int BK = Op<F16>::BK;
   constexpr int UMMA_K = Op<F16>::UMMA_K;
+  // the filter pass splits the 256 accumulator columns over two epilogue warpgroups; the sample
+  // pass keeps one (its per-query list lives in one thread's registers)
+  constexpr int EPI_WG = (MODE == MODE_FILTER) ? 2 : 1;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   // (offset arithmetic on the __shared__ pointer keeps its address space: LDS/STS, not generic LD/ST)
@@ -281,7 +356,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], 128 * EPI_WG);
       ptx::mbar_init(&abfull_bar[a], 1);
     }
     ptx::fence_barrier_init();
@@ -353,10 +428,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: 128 threads, thread <-> TMEM lane <-> query row of the tile =====
+  } else if (warp >= 4 && warp < 4 + 4 * EPI_WG) {
+    // ===== epilogue: EPI_WG warpgroups of 128 threads; thread <-> TMEM lane <-> query row of the
+    // tile; warpgroup g owns the column chunks [g*CPW, (g+1)*CPW) of every accumulator tile =====
+    constexpr int CPW = (TB / 32) / EPI_WG;          // 32-column chunks per warpgroup
     const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
     const int row_in_tile = quad * 32 + lane;
+    const int etid = wg * TQ + row_in_tile;          // index of this thread's private smem slots
     Sched<MODE> sch(p);
     int qt, t; bool first, last;
     int acc = 0; uint32_t acc_phase = 0;
@@ -382,28 +461,30 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       }
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
       ptx::tc_fence_after();
+      const int c0 = wg * CPW;                       // first chunk of this warpgroup
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
       const float* s_al = s_ab + acc * 2 * TB;
       const float* s_be = s_al + TB;
       const float4* al4 = reinterpret_cast<const float4*>(s_al);
       const float4* be4 = reinterpret_cast<const float4*>(s_be);
       const long long row0 = (long long)t * TB;
-      const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : TB / 32;
+      const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : CPW;
 
       // ---- fast path: one FFMA + compare per element, hits only recorded as bit masks ----
       // (the unrolled body stays small enough for the instruction cache; everything rare is
       //  in the single slow loop below, which re-reads the hit columns from TMEM)
       uint32_t va[32], vb[32];
-      uint32_t hit[TB / 32];
-      ptx::tmem_ld_32x32(taddr, va);
+      uint32_t hit[CPW];
+      ptx::tmem_ld_32x32(taddr + c0 * 32, va);
 #pragma unroll
-      for (int ch = 0; ch < TB / 32; ++ch) {
-        hit[ch] = 0;
-        if (MODE == MODE_SAMPLE && ch >= nch) continue;   // warp-uniform
+      for (int ci = 0; ci < CPW; ++ci) {
+        hit[ci] = 0;
+        if (MODE == MODE_SAMPLE && ci >= nch) continue;   // warp-uniform
+        const int ch = c0 + ci;
         ptx::tmem_wait_ld();
-        uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-        uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-        if (ch + 1 < TB / 32 && ch + 1 < nch) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
+        uint32_t(&cur)[32] = (ci & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (ci & 1) ? va : vb;
+        if (ci + 1 < CPW && ci + 1 < nch) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
         if (MODE == MODE_DUMP) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -419,7 +500,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
             if (fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z) < tau) mask |= 1u << (4 * j4 + 2);
             if (fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w) < tau) mask |= 1u << (4 * j4 + 3);
           }
-          hit[ch] = mask;
+          hit[ci] = mask;
         }
       }
       ptx::tmem_wait_ld();
@@ -428,18 +509,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (MODE != MODE_DUMP) {
         uint32_t anyhit = 0;
 #pragma unroll
-        for (int ch = 0; ch < TB / 32; ++ch) anyhit |= hit[ch];
+        for (int ci = 0; ci < CPW; ++ci) anyhit |= hit[ci];
         if (__any_sync(0xffffffffu, anyhit != 0)) {
 #pragma unroll
-          for (int ch = 0; ch < TB / 32; ++ch) s_mask[ch * TQ + row_in_tile] = hit[ch];   // thread-private slots
+          for (int ci = 0; ci < CPW; ++ci) s_mask[ci * (TQ * EPI_WG) + etid] = hit[ci];   // thread-private slots
 #pragma unroll 1
-          for (int ch = 0; ch < nch; ++ch) {
-            const uint32_t mine = s_mask[ch * TQ + row_in_tile];
+          for (int ci = 0; ci < nch; ++ci) {
+            const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
             uint32_t um = __reduce_or_sync(0xffffffffu, mine);
             while (um) {
               const int j = __ffs(um) - 1;
               um &= um - 1;
-              const int col = ch * 32 + j;
+              const int col = (c0 + ci) * 32 + j;
               const uint32_t v = ptx::tmem_ld_32x1(taddr + col);
               ptx::tmem_wait_ld();
               const float key = fmaf(s_be[col], __uint_as_float(v), s_al[col]);   // bit-identical to the fast path
@@ -447,14 +528,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
                 if (MODE == MODE_FILTER) {
                   // stage the record in this thread's private shared-memory slots; one global
                   // atomic reserves log space for a whole batch when the slots are full
-                  s_app[nst * TQ + row_in_tile] =
+                  s_app[nst * (TQ * EPI_WG) + etid] =
                       (static_cast<unsigned long long>(f2ord(key)) << 32) |
                       static_cast<unsigned long long>(row0 + col);
                   if (++nst == APPEND_SLOTS) {
                     const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
 #pragma unroll
                     for (int i = 0; i < APPEND_SLOTS; ++i)
-                      if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * TQ + row_in_tile];
+                      if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * (TQ * EPI_WG) + etid];
                     nst = 0;
                   }
                 } else {
@@ -470,15 +551,20 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           }
         }
       }
-      ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      if (MODE == MODE_SAMPLE && last && q < p.nq) p.tau[q] = tau;
+      if (MODE == MODE_SAMPLE && last && q < p.nq) {
+        // this CTA covered one half of the query tile's sample: publish its list, tau_merge_kernel
+        // takes the SAMPLE_M-th smallest of the union
+        float* dst = p.slist + (q * 2 + (sch.u & 1)) * SAMPLE_M;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_M; ++j) dst[j] = lst[j];
+      }
       if (MODE == MODE_FILTER && last && nst > 0) {
         const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)nst);
         for (int j = 0; j < nst; ++j)
-          if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * TQ + row_in_tile];
+          if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * (TQ * EPI_WG) + etid];
         nst = 0;
       }
     }
@@ -499,7 +585,11 @@ struct FinParams {
   const float* base; const float* query;
   long long nb, nq; int d, k, metric;
   long long id_offset;
-  const float* tau; const unsigned int* cnt; const unsigned long long* log;
+  const float* tau; const unsigned int* cnt;
+  unsigned long long* log;     // [nq][LOG_CAP]; select rewrites [0,R) sorted, rerank writes fp64 at [LOG_CAP/2, LOG_CAP/2+R)
+  int* rr;                     // [nq] rows to re-rank, -1 = uncertified
+  float* epsq;                 // [nq] proven key error bound
+  double* qn2;                 // [nq] |q|^2
   Scalars* sc;
   float c_rel;                 // relative error constant of the operand format
   int f16;                     // fp16 operands: adds the subnormal-quantisation term
@@ -507,68 +597,40 @@ struct FinParams {
   int* fail_list;
 };
 
-// fp64 distance of one base row to the query held in shared memory, computed by one warp.
-// Same operation order as scan_dist_kernel so both exact paths agree bit for bit.
-__device__ __forceinline__ double warp_exact_distance(int metric, const float* s_q, const float* brow,
-                                                      int d, double qn2, int lane) {
-  double acc = 0.0, bn2 = 0.0;
-  for (int c = lane * 4; c < d; c += 128) {
-    float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
-    float4 q4 = *reinterpret_cast<const float4*>(s_q + c);
-    double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
-    if (metric == NWK_METRIC_COSINE) {
-      bn2 = fma(b0, b0, bn2); bn2 = fma(b1, b1, bn2); bn2 = fma(b2, b2, bn2); bn2 = fma(b3, b3, bn2);
-    }
-    if (metric == NWK_METRIC_SQEUCLIDEAN) {
-      double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
-      acc = fma(e0, e0, acc); acc = fma(e1, e1, acc); acc = fma(e2, e2, acc); acc = fma(e3, e3, acc);
-    } else {
-      acc = fma((double)q4.x, b0, acc); acc = fma((double)q4.y, b1, acc);
-      acc = fma((double)q4.z, b2, acc); acc = fma((double)q4.w, b3, acc);
-    }
-  }
-  acc = warp_sum(acc);
-  if (metric == NWK_METRIC_SQEUCLIDEAN) return acc;
-  if (metric == NWK_METRIC_COSINE) bn2 = warp_sum(bn2);
-  return finish_metric(metric, acc, qn2, bn2);
-}
+constexpr int SEL_THREADS = 256;
+constexpr int RR_THREADS = 256;
+constexpr int RR_ROWS = 4;                       // candidate rows in flight per warp
+constexpr int RR_BLOCK_ROWS = (RR_THREADS / 32) * RR_ROWS;
+constexpr int OUT_THREADS = 128;
 
-__global__ void __launch_bounds__(FIN_THREADS)
-finish_kernel(const FinParams p) {
-  extern __shared__ __align__(16) unsigned char fin_smem[];
-  // [LOG_CAP] packed (key, row) records; once sorted only the first R <= RERANK_MAX are needed,
-  // so the fp64 (distance, id) arrays of the re-rank live in the tail of the same buffer
-  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(fin_smem);
-  double* s_key = reinterpret_cast<double*>(fin_smem + RERANK_MAX * 8);
-  long long* s_id = reinterpret_cast<long long*>(fin_smem + RERANK_MAX * 8 + RERANK_MAX * 8);
-  float* s_q = reinterpret_cast<float*>(fin_smem + LOG_CAP * 8);                            // [d]
+// select: sort the query's log, find the band [a_k, a_k + 2 eps], certify, keep the R rows in it
+__global__ void __launch_bounds__(SEL_THREADS)
+select_kernel(const FinParams p) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(sel_smem);             // [LOG_CAP]
   __shared__ double s_qn2;
-  __shared__ double s_eps;
   __shared__ int s_R;
-  __shared__ int s_fail;
-  __shared__ float s_ratio[FIN_THREADS / 32];
 
   const long long q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned int total = p.cnt[q];
   const int c = (int)min(total, (unsigned int)LOG_CAP);
   const int n2 = max(next_pow2(c), 2);
+  unsigned long long* glog = p.log + q * LOG_CAP;
 
-  for (int i = threadIdx.x; i < n2; i += blockDim.x)
-    s_log[i] = (i < c) ? p.log[q * LOG_CAP + i] : ~0ull;
-  for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.query[q * p.d + i];
-  block_bitonic_sort_u64(s_log, n2);      // (contains the __syncthreads the loads above need)
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) s_log[i] = (i < c) ? glog[i] : ~0ull;
   if (warp == 0) {
     // |q|^2 in the same operation order as scan_dist_kernel
     double a = 0.0;
-    for (int c2 = lane; c2 < p.d; c2 += 32) { double v = s_q[c2]; a = fma(v, v, a); }
+    const float* qrow = p.query + q * p.d;
+    for (int c2 = lane; c2 < p.d; c2 += 32) { double v = qrow[c2]; a = fma(v, v, a); }
     a = warp_sum(a);
     if (lane == 0) s_qn2 = a;
   }
-  __syncthreads();
-  const double qn2 = s_qn2;
+  block_bitonic_sort_u64(s_log, n2);
 
   if (threadIdx.x == 0) {
+    const double qn2 = s_qn2;
     int fail = 0, R = 0;
     double eps = 0.0;
     if (total > (unsigned int)LOG_CAP || c < p.k) {
@@ -605,9 +667,6 @@ finish_kernel(const FinParams p) {
       R = lo;
       if (R > RERANK_MAX) { fail = 1; R = RERANK_MAX; }
     }
-    s_fail = fail;
-    s_R = R;
-    s_eps = eps;
     atomicAdd(p.sc->stat_sum + 0, (unsigned long long)total);
     atomicAdd(p.sc->stat_sum + 1, (unsigned long long)R);
     atomicMax(p.sc->stat_max + 0, total);
@@ -616,44 +675,50 @@ finish_kernel(const FinParams p) {
       int slot = atomicAdd(&p.sc->fail_cnt, 1);
       p.fail_list[slot] = (int)q;
     }
+    p.rr[q] = fail ? -1 : R;
+    p.epsq[q] = (float)eps;
+    p.qn2[q] = qn2;
+    s_R = fail ? 0 : R;
   }
   __syncthreads();
-  if (s_fail) return;
   const int R = s_R;
-  const int r2 = max(next_pow2(R), 2);
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  const double eps = s_eps;
-  // exact key = (distance - key_shift) * key_scale: the candidate keys omit the per-query
-  // constants (|q|^2 for sq-L2, the 1 of cosine / dot, and cosine's 1/|q|)
-  const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
-  const double key_scale = (p.metric == NWK_METRIC_COSINE) ? sqrt(qn2) : 1.0;
-  float ratio = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) glog[i] = s_log[i];
+}
 
-  // each warp keeps FIN_ROWS candidate rows in flight (independent loads) per iteration
-  constexpr int FIN_ROWS = 4;
-  for (int i0 = warp * FIN_ROWS; i0 < r2; i0 += (FIN_THREADS / 32) * FIN_ROWS) {
-    long long rows[FIN_ROWS];
-    float akey[FIN_ROWS];
-    double acc[FIN_ROWS], bn2[FIN_ROWS];
+// rerank: fp64 distance of every kept row, RR_ROWS rows in flight per warp (HBM gather bound)
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_kernel(const FinParams p) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  float* s_q = reinterpret_cast<float*>(rr_smem);                                           // [d]
+  const long long q = blockIdx.x;
+  const int R = p.rr[q];
+  if (R <= 0 || (int)blockIdx.y * RR_BLOCK_ROWS >= R) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x * 4; i < p.d; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(s_q + i) = __ldg(reinterpret_cast<const float4*>(p.query + q * p.d + i));
+  __syncthreads();
+  const double qn2 = p.qn2[q];
+  const unsigned long long* glog = p.log + q * LOG_CAP;
+  double* gdist = reinterpret_cast<double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
+
+  for (int i0 = blockIdx.y * RR_BLOCK_ROWS + warp * RR_ROWS; i0 < R; i0 += gridDim.y * RR_BLOCK_ROWS) {
+    long long rows[RR_ROWS];
+    double acc[RR_ROWS], bn2[RR_ROWS];
 #pragma unroll
-    for (int r = 0; r < FIN_ROWS; ++r) {
-      rows[r] = -1; akey[r] = 0.f; acc[r] = 0.0; bn2[r] = 0.0;
-      if (i0 + r < R) {
-        const unsigned long long rec = s_log[i0 + r];
-        rows[r] = (long long)(rec & 0xffffffffull);
-        akey[r] = ord2f((uint32_t)(rec >> 32));
-      }
+    for (int r = 0; r < RR_ROWS; ++r) {
+      acc[r] = 0.0; bn2[r] = 0.0;
+      rows[r] = (i0 + r < R) ? (long long)(glog[i0 + r] & 0xffffffffull) : -1;
     }
     for (int c2 = lane * 4; c2 < p.d; c2 += 128) {
       const float4 q4 = *reinterpret_cast<const float4*>(s_q + c2);
-      float4 b4[FIN_ROWS];
+      float4 b4[RR_ROWS];
 #pragma unroll
-      for (int r = 0; r < FIN_ROWS; ++r)
+      for (int r = 0; r < RR_ROWS; ++r)
         b4[r] = rows[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.base + rows[r] * p.d + c2))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < FIN_ROWS; ++r) {
-        // same operation order as warp_exact_distance / scan_dist_kernel
+      for (int r = 0; r < RR_ROWS; ++r) {
+        // same operation order as scan_dist_kernel: both exact paths agree bit for bit
         const double b0 = b4[r].x, b1 = b4[r].y, b2 = b4[r].z, b3 = b4[r].w;
         if (p.metric == NWK_METRIC_COSINE) {
           bn2[r] = fma(b0, b0, bn2[r]); bn2[r] = fma(b1, b1, bn2[r]);
@@ -670,21 +735,55 @@ finish_kernel(const FinParams p) {
       }
     }
 #pragma unroll
-    for (int r = 0; r < FIN_ROWS; ++r) {
+    for (int r = 0; r < RR_ROWS; ++r) {
       double dist = warp_sum(acc[r]);
       if (p.metric == NWK_METRIC_COSINE) bn2[r] = warp_sum(bn2[r]);
       if (p.metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(p.metric, dist, qn2, bn2[r]);
-      if (rows[r] < 0) dist = INF;
-      else if (dist == dist) ratio = fmaxf(ratio, (float)(fabs((double)akey[r] - (dist - key_shift) * key_scale) / eps));
-      else dist = INF;
-      // s_key / s_id alias s_log[RERANK_MAX ..): disjoint from the R <= RERANK_MAX records read above
-      if (lane == 0 && i0 + r < r2) {
-        s_key[i0 + r] = dist;
-        s_id[i0 + r] = rows[r] >= 0 ? rows[r] : 0x7fffffffffffffffLL;
-      }
+      if (lane == 0 && rows[r] >= 0) gdist[i0 + r] = dist;
     }
   }
-  if (lane == 0) s_ratio[warp] = ratio;
+}
+
+// output: order the re-ranked rows by (fp64 distance, index), emit k, monitor the error bound
+__global__ void __launch_bounds__(OUT_THREADS)
+output_kernel(const FinParams p) {
+  __shared__ double s_key[RERANK_MAX];
+  __shared__ long long s_id[RERANK_MAX];
+  __shared__ float s_ratio[OUT_THREADS / 32];
+  const long long q = blockIdx.x;
+  const int R = p.rr[q];
+  if (R <= 0) return;
+  const int r2 = max(next_pow2(R), 2);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const unsigned long long* glog = p.log + q * LOG_CAP;
+  const double* gdist = reinterpret_cast<const double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
+  const double qn2 = p.qn2[q];
+  const double eps = (double)p.epsq[q];
+  // exact key = (distance - key_shift) * key_scale: the candidate keys omit the per-query
+  // constants (|q|^2 for sq-L2, the 1 of cosine / dot, and cosine's 1/|q|)
+  const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
+  const double key_scale = (p.metric == NWK_METRIC_COSINE) ? sqrt(qn2) : 1.0;
+  float ratio = 0.f;
+  for (int i = threadIdx.x; i < r2; i += blockDim.x) {
+    double dist = INF;
+    long long id = 0x7fffffffffffffffLL;
+    if (i < R) {
+      const unsigned long long rec = glog[i];
+      id = (long long)(rec & 0xffffffffull);
+      dist = gdist[i];
+      if (dist == dist) {
+        const float akey = ord2f((uint32_t)(rec >> 32));
+        ratio = fmaxf(ratio, (float)(fabs((double)akey - (dist - key_shift) * key_scale) / eps));
+      } else {
+        dist = INF;
+      }
+    }
+    s_key[i] = dist;
+    s_id[i] = id;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+  if ((threadIdx.x & 31) == 0) s_ratio[threadIdx.x >> 5] = ratio;
   block_bitonic_sort(s_key, s_id, r2);
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
     p.out_dist[q * p.k + j] = (float)s_key[j];
@@ -692,7 +791,7 @@ finish_kernel(const FinParams p) {
   }
   if (threadIdx.x == 0) {
     float r = 0.f;
-    for (int w = 0; w < FIN_THREADS / 32; ++w) r = fmaxf(r, s_ratio[w]);
+    for (int w = 0; w < OUT_THREADS / 32; ++w) r = fmaxf(r, s_ratio[w]);
     atomicMax(&p.sc->err_ratio, __float_as_uint(r));
   }
 }
@@ -803,7 +902,9 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
   bytes += align_up((size_t)nq * 4, 256);                   // cnt
   bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
-  bytes += align_up((size_t)nq * 4, 256);                   // fail list
+  bytes += align_up((size_t)nq * 4, 256) * 3;               // fail list, rows-to-rerank, eps
+  bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
+  bytes += align_up((size_t)nq * 2 * SAMPLE_M * 4, 256);    // half-sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
   bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
   bytes += 4096;                                            // scalars
@@ -836,6 +937,10 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   unsigned int* cnt = ar.take<unsigned int>((size_t)nq);
   unsigned long long* log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
   int* fail_list = ar.take<int>((size_t)nq);
+  int* rr = ar.take<int>((size_t)nq);
+  float* epsq = ar.take<float>((size_t)nq);
+  double* qn2 = ar.take<double>((size_t)nq);
+  float* slist = ar.take<float>((size_t)nq * 2 * SAMPLE_M);
   __half* bh = ar.take<__half>((size_t)nb * pl.dh);
   __half* qh = ar.take<__half>((size_t)nq * pl.dh);
   Scalars* sc = ar.take<Scalars>(1);
@@ -881,11 +986,15 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   TcParams p{};
   p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks;
-  p.alpha = alpha; p.beta = beta; p.tau = tau; p.cnt = cnt; p.log = log; p.err = &sc->err;
+  p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
 
   if (pl.sample) {
-    int grid = pl.nQT < sms ? pl.nQT : sms;
+    fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * 2 * SAMPLE_M, HUGE_VALF);
+    NWK_LAUNCH_CHECK();
+    int grid = 2 * pl.nQT < sms ? 2 * pl.nQT : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_b, p, s));
+    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, tau);
+    NWK_LAUNCH_CHECK();
   } else {
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
     NWK_LAUNCH_CHECK();
@@ -900,6 +1009,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   FinParams f{};
   f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
   f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
+  f.rr = rr; f.epsq = epsq; f.qn2 = qn2;
   // Relative error of acc against sum |q_i b_i| <= |q||b|:
   //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
   //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
@@ -908,13 +1018,24 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
   f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   {
-    const int fin_smem = LOG_CAP * 8 + d * 4 + 16;
-    static int fin_optin = 0;
-    if (fin_smem > fin_optin) {
-      NWK_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem));
-      fin_optin = fin_smem;
+    static bool sel_optin = false;
+    if (!sel_optin) {
+      NWK_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOG_CAP * 8));
+      sel_optin = true;
     }
-    finish_kernel<<<(unsigned)nq, FIN_THREADS, fin_smem, s>>>(f);
+    select_kernel<<<(unsigned)nq, SEL_THREADS, LOG_CAP * 8, s>>>(f);
+    NWK_LAUNCH_CHECK();
+    const int rr_smem = (d + 3) / 4 * 16;
+    static int rr_optin = 48 * 1024;
+    if (rr_smem > rr_optin) {
+      NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
+      rr_optin = rr_smem;
+    }
+    // grid.y blocks of 32 rows each stride over the query's R rows (R is only known on the device)
+    dim3 rgrid((unsigned)nq, 8);
+    rerank_kernel<<<rgrid, RR_THREADS, rr_smem, s>>>(f);
+    NWK_LAUNCH_CHECK();
+    output_kernel<<<(unsigned)nq, OUT_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[4], s);
