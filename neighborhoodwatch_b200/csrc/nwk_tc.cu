@@ -82,7 +82,7 @@ struct TcParams {
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
-  int nS, sChunks;          // SAMPLE: sample tiles, 32-column chunks used per sample tile
+  int nS, sChunks, sParts;  // SAMPLE: sample tiles, 32-column chunks used per tile, parts per query tile (1 or 2)
   const float* alpha;       // [nT*TB]
   const float* beta;        // [nT*TB]
   float* tau;               // [nQT*TQ]
@@ -278,10 +278,10 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 // ---------------------------------------------------------------------------------------
 template <int MODE>
 struct Sched {
-  int nUnits, nQT, nT, G, nS, dump_qt, dump_t;
+  int nUnits, nQT, nT, G, nS, sParts, dump_qt, dump_t;
   int u, i, len, qt, c;
   __device__ explicit Sched(const TcParams& p)
-      : nUnits(p.nUnits), nQT(p.nQT), nT(p.nT), G(p.G), nS(p.nS), dump_qt(p.dump_qt), dump_t(p.dump_t),
+      : nUnits(p.nUnits), nQT(p.nQT), nT(p.nT), G(p.G), nS(p.nS), sParts(p.sParts), dump_qt(p.dump_qt), dump_t(p.dump_t),
         u((int)blockIdx.x - (int)gridDim.x), i(0), len(0), qt(0), c(0) {}
   // advance to the next pair; returns false when the CTA is done
   __device__ __forceinline__ bool next(int& out_qt, int& out_t, bool& first, bool& last) {
@@ -293,14 +293,15 @@ struct Sched {
         qt = u - c * nQT;
         len = min(G, nT - c * G);
       } else if (MODE == MODE_SAMPLE) {
-        // unit = (query tile, half of the sample tiles): 2*nQT units keep every SM busy;
-        // an empty half (nS == 1) is skipped, its list stays at the +inf it was filled with
+        // unit = (query tile, part of the sample tiles); parts > 1 only when there are far fewer
+        // query tiles than SMs (every part pays the warm-up of its own list)
         do {
           u += gridDim.x;
-          if (u >= 2 * nQT) return false;
-          qt = u >> 1;
-          c = (u & 1) ? (nS + 1) / 2 : 0;
-          len = (u & 1) ? nS - c : (nS + 1) / 2;
+          if (u >= sParts * nQT) return false;
+          qt = u / sParts;
+          const int part = u - qt * sParts;
+          c = (int)(((long long)part * nS) / sParts);
+          len = (int)(((long long)(part + 1) * nS) / sParts) - c;
         } while (len == 0);
       } else {
         u += gridDim.x;
@@ -518,33 +519,45 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
             const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
             uint32_t um = __reduce_or_sync(0xffffffffu, mine);
             while (um) {
-              const int j = __ffs(um) - 1;
-              um &= um - 1;
-              const int col = (c0 + ci) * 32 + j;
-              const uint32_t v = ptx::tmem_ld_32x1(taddr + col);
+              // up to 4 hit columns per round: their TMEM loads are issued back to back and
+              // waited for once (the load latency, not the arithmetic, is the cost here)
+              int jj[4];
+              uint32_t vv[4];
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                jj[b] = um ? __ffs(um) - 1 : -1;
+                um &= um - 1;                        // (0 & anything stays 0)
+                if (jj[b] >= 0) vv[b] = ptx::tmem_ld_32x1(taddr + (c0 + ci) * 32 + jj[b]);   // warp-uniform
+              }
               ptx::tmem_wait_ld();
-              const float key = fmaf(s_be[col], __uint_as_float(v), s_al[col]);   // bit-identical to the fast path
-              if (((mine >> j) & 1u) && key < tau) {
-                if (MODE == MODE_FILTER) {
-                  // stage the record in this thread's private shared-memory slots; one global
-                  // atomic reserves log space for a whole batch when the slots are full
-                  s_app[nst * (TQ * EPI_WG) + etid] =
-                      (static_cast<unsigned long long>(f2ord(key)) << 32) |
-                      static_cast<unsigned long long>(row0 + col);
-                  if (++nst == APPEND_SLOTS) {
-                    const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
 #pragma unroll
-                    for (int i = 0; i < APPEND_SLOTS; ++i)
-                      if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * (TQ * EPI_WG) + etid];
-                    nst = 0;
+              for (int b = 0; b < 4; ++b) {
+                if (jj[b] < 0) continue;             // warp-uniform
+                const int j = jj[b];
+                const int col = (c0 + ci) * 32 + j;
+                const float key = fmaf(s_be[col], __uint_as_float(vv[b]), s_al[col]);   // bit-identical to the fast path
+                if (((mine >> j) & 1u) && key < tau) {
+                  if (MODE == MODE_FILTER) {
+                    // stage the record in this thread's private shared-memory slots; one global
+                    // atomic reserves log space for a whole batch when the slots are full
+                    s_app[nst * (TQ * EPI_WG) + etid] =
+                        (static_cast<unsigned long long>(f2ord(key)) << 32) |
+                        static_cast<unsigned long long>(row0 + col);
+                    if (++nst == APPEND_SLOTS) {
+                      const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
+#pragma unroll
+                      for (int i = 0; i < APPEND_SLOTS; ++i)
+                        if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * (TQ * EPI_WG) + etid];
+                      nst = 0;
+                    }
+                  } else {
+                    // insert into the ascending register list and drop the largest:
+                    // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
+#pragma unroll
+                    for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
+                    lst[0] = fminf(lst[0], key);
+                    tau = lst[SAMPLE_M - 1];
                   }
-                } else {
-                  // insert into the ascending register list and drop the largest:
-                  // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
-#pragma unroll
-                  for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
-                  lst[0] = fminf(lst[0], key);
-                  tau = lst[SAMPLE_M - 1];
                 }
               }
             }
@@ -557,7 +570,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (MODE == MODE_SAMPLE && last && q < p.nq) {
         // this CTA covered one half of the query tile's sample: publish its list, tau_merge_kernel
         // takes the SAMPLE_M-th smallest of the union
-        float* dst = p.slist + (q * 2 + (sch.u & 1)) * SAMPLE_M;
+        float* dst = p.slist + (q * 2 + (sch.u % sch.sParts)) * SAMPLE_M;
 #pragma unroll
         for (int j = 0; j < SAMPLE_M; ++j) dst[j] = lst[j];
       }
@@ -856,7 +869,7 @@ bool tc_path_supported(long long nb, long long nq, int d, int k) {
 }
 
 struct TcPlan {
-  int nQT, nT, nKB, G, nChunks, nUnits, nS, sChunks, dh;
+  int nQT, nT, nKB, G, nChunks, nUnits, nS, sChunks, sParts, dh;
   bool sample;
   long long nb_pad, nq_pad;
 };
@@ -891,6 +904,7 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
     if (ns < 1) ns = 1;
     pl.nS = (int)ns;
     pl.sChunks = (int)(cols / 32);
+    pl.sParts = (2 * pl.nQT <= sms && pl.nS >= 2) ? 2 : 1;
   }
   return pl;
 }
@@ -985,13 +999,13 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
 
   TcParams p{};
   p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
-  p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks;
+  p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
 
   if (pl.sample) {
     fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * 2 * SAMPLE_M, HUGE_VALF);
     NWK_LAUNCH_CHECK();
-    int grid = 2 * pl.nQT < sms ? 2 * pl.nQT : sms;
+    int grid = pl.sParts * pl.nQT < sms ? pl.sParts * pl.nQT : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_b, p, s));
     tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, tau);
     NWK_LAUNCH_CHECK();
