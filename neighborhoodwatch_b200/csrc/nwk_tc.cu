@@ -271,6 +271,22 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
     p[i] = v;
 }
 
+// Stage one candidate record in the calling thread's private shared-memory slots (slot i at
+// slots[i * stride]); when all APPEND_SLOTS are used, one global atomic reserves log space for
+// the batch and the records are written out.  Returns the new number of staged records.
+__device__ __noinline__ int append_record(unsigned long long rec, int nst, unsigned long long* slots, int stride,
+                                          unsigned int* cnt, unsigned long long* qlog) {
+  slots[nst * stride] = rec;
+  if (++nst == APPEND_SLOTS) {
+    const unsigned int base = atomicAdd(cnt, (unsigned int)APPEND_SLOTS);
+#pragma unroll
+    for (int i = 0; i < APPEND_SLOTS; ++i)
+      if (base + i < LOG_CAP) qlog[base + i] = slots[i * stride];
+    nst = 0;
+  }
+  return nst;
+}
+
 // ---------------------------------------------------------------------------------------
 // schedule shared by the three roles of tc_kernel: the sequence of (query tile, base tile)
 // pairs this CTA walks, in an order that keeps concurrently running CTAs on the same base
@@ -357,7 +373,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128 * EPI_WG);
+      ptx::mbar_init(&tempty_bar[a], 4 * EPI_WG);
       ptx::mbar_init(&abfull_bar[a], 1);
     }
     ptx::fence_barrier_init();
@@ -507,7 +523,38 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       ptx::tmem_wait_ld();
 
       // ---- slow path (rare): columns where some lane of the warp has a hit ----
-      if (MODE != MODE_DUMP) {
+      if (MODE == MODE_FILTER) {
+        // unrolled over this warpgroup's chunks so the hit masks stay in registers; the
+        // append itself is one out-of-line function (keeps the loop body in the I-cache)
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const uint32_t mine = hit[ci];
+          uint32_t um = __reduce_or_sync(0xffffffffu, mine);
+          while (um) {
+            // up to 4 hit columns per round: their TMEM loads are issued back to back and
+            // waited for once (the load latency, not the arithmetic, is the cost here)
+            int jj[4];
+            uint32_t vv[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              jj[b] = um ? __ffs(um) - 1 : -1;
+              um &= um - 1;                          // (0 & anything stays 0)
+              if (jj[b] >= 0) vv[b] = ptx::tmem_ld_32x1(taddr + (c0 + ci) * 32 + jj[b]);   // warp-uniform
+            }
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (jj[b] < 0) continue;               // warp-uniform
+              const int col = (c0 + ci) * 32 + jj[b];
+              const float key = fmaf(s_be[col], __uint_as_float(vv[b]), s_al[col]);   // bit-identical to the fast path
+              if (((mine >> jj[b]) & 1u) && key < tau)
+                nst = append_record((static_cast<unsigned long long>(f2ord(key)) << 32) |
+                                        static_cast<unsigned long long>(row0 + col),
+                                    nst, s_app + etid, TQ * EPI_WG, p.cnt + q, p.log + q * LOG_CAP);
+            }
+          }
+        }
+      } else if (MODE == MODE_SAMPLE) {
         uint32_t anyhit = 0;
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) anyhit |= hit[ci];
@@ -519,53 +566,27 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
             const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
             uint32_t um = __reduce_or_sync(0xffffffffu, mine);
             while (um) {
-              // up to 4 hit columns per round: their TMEM loads are issued back to back and
-              // waited for once (the load latency, not the arithmetic, is the cost here)
-              int jj[4];
-              uint32_t vv[4];
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                jj[b] = um ? __ffs(um) - 1 : -1;
-                um &= um - 1;                        // (0 & anything stays 0)
-                if (jj[b] >= 0) vv[b] = ptx::tmem_ld_32x1(taddr + (c0 + ci) * 32 + jj[b]);   // warp-uniform
-              }
+              const int j = __ffs(um) - 1;
+              um &= um - 1;
+              const int col = (c0 + ci) * 32 + j;
+              const uint32_t v = ptx::tmem_ld_32x1(taddr + col);
               ptx::tmem_wait_ld();
+              const float key = fmaf(s_be[col], __uint_as_float(v), s_al[col]);   // bit-identical to the fast path
+              if (((mine >> j) & 1u) && key < tau) {
+                // insert into the ascending register list and drop the largest:
+                // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
 #pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                if (jj[b] < 0) continue;             // warp-uniform
-                const int j = jj[b];
-                const int col = (c0 + ci) * 32 + j;
-                const float key = fmaf(s_be[col], __uint_as_float(vv[b]), s_al[col]);   // bit-identical to the fast path
-                if (((mine >> j) & 1u) && key < tau) {
-                  if (MODE == MODE_FILTER) {
-                    // stage the record in this thread's private shared-memory slots; one global
-                    // atomic reserves log space for a whole batch when the slots are full
-                    s_app[nst * (TQ * EPI_WG) + etid] =
-                        (static_cast<unsigned long long>(f2ord(key)) << 32) |
-                        static_cast<unsigned long long>(row0 + col);
-                    if (++nst == APPEND_SLOTS) {
-                      const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
-#pragma unroll
-                      for (int i = 0; i < APPEND_SLOTS; ++i)
-                        if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = s_app[i * (TQ * EPI_WG) + etid];
-                      nst = 0;
-                    }
-                  } else {
-                    // insert into the ascending register list and drop the largest:
-                    // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
-#pragma unroll
-                    for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
-                    lst[0] = fminf(lst[0], key);
-                    tau = lst[SAMPLE_M - 1];
-                  }
-                }
+                for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
+                lst[0] = fminf(lst[0], key);
+                tau = lst[SAMPLE_M - 1];
               }
             }
           }
         }
       }
+      __syncwarp();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // one arrival per epilogue warp
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       if (MODE == MODE_SAMPLE && last && q < p.nq) {
         // this CTA covered one half of the query tile's sample: publish its list, tau_merge_kernel
