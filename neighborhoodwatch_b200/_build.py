@@ -39,18 +39,23 @@ def _stale() -> bool:
     return any(os.path.getmtime(p) > lib_m for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a into one shared library; returns its path."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out_path: str = None) -> str:
+    """Compile every .cu for sm_100a into one shared library; returns its path.
+
+    ``defines`` / ``out_path`` build an experiment variant (extra -D macros) next to the
+    product library; the product build uses neither.
+    """
+    global_out = out_path or LIB_PATH
+    if not force and not defines and not _stale():
         return LIB_PATH
     nvcc = _nvcc()
-    obj_dir = os.path.join(PKG_DIR, "build")
+    obj_dir = os.path.join(PKG_DIR, "build" if not defines else "build_" + os.path.basename(global_out))
     os.makedirs(obj_dir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -66,11 +71,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed; see output above")
     if verbose:
         print("\n".join(log))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH + ".tmp", *objs,
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", global_out + ".tmp", *objs,
             "-cudart", "static"]
     subprocess.run(link, check=True)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(global_out + ".tmp", global_out)
+    return global_out
 
 
 if __name__ == "__main__":

@@ -61,8 +61,8 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or (_build._stale() and _can_build()):
+    path = os.environ.get("NWK_LIB_PATH") or _build.LIB_PATH     # NWK_LIB_PATH: experiment builds only
+    if path == _build.LIB_PATH and (not os.path.exists(path) or (_build._stale() and _can_build())):
         _build.build()
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing and could not be built; there is no CPU fallback")

@@ -67,6 +67,18 @@ constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
 constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
 constexpr int TC_MAX_K = 256;
+#ifndef NWK_SLOW_BATCH
+#define NWK_SLOW_BATCH 1          // hit columns whose TMEM loads are in flight together (1 = one at a time)
+#endif
+#ifndef NWK_WARP_ARRIVE
+#define NWK_WARP_ARRIVE 1         // 1: one tempty arrival per epilogue warp, 0: one per thread
+#endif
+#ifndef NWK_APPEND_NOINLINE
+#define NWK_APPEND_NOINLINE 0     // measured: an out-of-line call costs +11 % at d=128 (register save/restore)
+#endif
+#ifndef NWK_SLOW_DYNAMIC
+#define NWK_SLOW_DYNAMIC 0        // 1: filter slow path as one rolled loop over chunks (masks via smem)
+#endif
 
 enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
 enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
@@ -274,7 +286,12 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 // Stage one candidate record in the calling thread's private shared-memory slots (slot i at
 // slots[i * stride]); when all APPEND_SLOTS are used, one global atomic reserves log space for
 // the batch and the records are written out.  Returns the new number of staged records.
-__device__ __noinline__ int append_record(unsigned long long rec, int nst, unsigned long long* slots, int stride,
+#if NWK_APPEND_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+int append_record(unsigned long long rec, int nst, unsigned long long* slots, int stride,
                                           unsigned int* cnt, unsigned long long* qlog) {
   slots[nst * stride] = rec;
   if (++nst == APPEND_SLOTS) {
@@ -373,7 +390,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4 * EPI_WG);
+      ptx::mbar_init(&tempty_bar[a], (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG);
       ptx::mbar_init(&abfull_bar[a], 1);
     }
     ptx::fence_barrier_init();
@@ -526,24 +543,37 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (MODE == MODE_FILTER) {
         // unrolled over this warpgroup's chunks so the hit masks stay in registers; the
         // append itself is one out-of-line function (keeps the loop body in the I-cache)
+#if NWK_SLOW_DYNAMIC
+        uint32_t anyhit = 0;
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) anyhit |= hit[ci];
+        if (__any_sync(0xffffffffu, anyhit != 0)) {
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) s_mask[ci * (TQ * EPI_WG) + etid] = hit[ci];
+#pragma unroll 1
+        for (int ci = 0; ci < CPW; ++ci) {
+          const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
+#else
+        {
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
           const uint32_t mine = hit[ci];
+#endif
           uint32_t um = __reduce_or_sync(0xffffffffu, mine);
           while (um) {
             // up to 4 hit columns per round: their TMEM loads are issued back to back and
             // waited for once (the load latency, not the arithmetic, is the cost here)
-            int jj[4];
-            uint32_t vv[4];
+            int jj[NWK_SLOW_BATCH];
+            uint32_t vv[NWK_SLOW_BATCH];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < NWK_SLOW_BATCH; ++b) {
               jj[b] = um ? __ffs(um) - 1 : -1;
               um &= um - 1;                          // (0 & anything stays 0)
               if (jj[b] >= 0) vv[b] = ptx::tmem_ld_32x1(taddr + (c0 + ci) * 32 + jj[b]);   // warp-uniform
             }
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < NWK_SLOW_BATCH; ++b) {
               if (jj[b] < 0) continue;               // warp-uniform
               const int col = (c0 + ci) * 32 + jj[b];
               const float key = fmaf(s_be[col], __uint_as_float(vv[b]), s_al[col]);   // bit-identical to the fast path
@@ -553,6 +583,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
                                     nst, s_app + etid, TQ * EPI_WG, p.cnt + q, p.log + q * LOG_CAP);
             }
           }
+        }
         }
       } else if (MODE == MODE_SAMPLE) {
         uint32_t anyhit = 0;
@@ -586,7 +617,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       }
       __syncwarp();
       ptx::tc_fence_before();
+#if NWK_WARP_ARRIVE
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // one arrival per epilogue warp
+#else
+      ptx::mbar_arrive(&tempty_bar[acc]);
+#endif
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       if (MODE == MODE_SAMPLE && last && q < p.nq) {
         // this CTA covered one half of the query tile's sample: publish its list, tau_merge_kernel
