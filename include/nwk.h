@@ -161,6 +161,15 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
 int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0,
                    int32_t normalize, void* stream);
 
+/* Post-validator with the reference's acceptance rule (parquet_to_format.py:351-383): for every
+ * query q and returned neighbour j, numpy.isclose(1 - dot(query_q, base[idx[q,j]]), dist[q,j] / 2)
+ * (squared L2 on unit vectors; the reference's defaults are rtol = 1e-5, atol = 1e-8); zero query
+ * vectors are skipped as there.  All pointers are device memory except mismatches_host, which
+ * receives the number of violating pairs (the call synchronises the stream). */
+int nwk_validate_pairs(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d,
+                       const int64_t* idx, const float* dist, int32_t k, double rtol, double atol,
+                       int64_t* mismatches_host, void* stream);
+
 /* Diagnostics used by the parity tests: raw tensor-core dot products (fp16 or TF32 operands) of one
  * 128 x 256 tile pair (query rows q0.., base rows b0..) written to out[128*256] fp32,
  * so the tcgen05 / TMA descriptors can be validated in isolation. */

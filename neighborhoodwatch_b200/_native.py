@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "nwk_last_error", "nwk_abi_version", "nwk_launch_count", "nwk_knn_workspace_bytes", "nwk_knn_f32",
     "nwk_merge_workspace_bytes", "nwk_merge_topk", "nwk_topk_state_create", "nwk_topk_state_update",
     "nwk_topk_state_finalize", "nwk_topk_state_destroy", "nwk_knn_host_f32", "nwk_synth_fill",
-    "nwk_debug_tc_tile",
+    "nwk_debug_tc_tile", "nwk_validate_pairs",
 )
 
 
@@ -97,6 +97,9 @@ def load() -> ctypes.CDLL:
     lib.nwk_debug_tc_tile.restype = c_int32
     lib.nwk_debug_tc_tile.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p,
                                       c_int32, c_void_p]
+    lib.nwk_validate_pairs.restype = c_int32
+    lib.nwk_validate_pairs.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32,
+                                       ctypes.c_double, ctypes.c_double, POINTER(c_int64), c_void_p]
     if lib.nwk_abi_version() != 1:
         raise ImportError(f"{path}: ABI version {lib.nwk_abi_version()} != 1")
     _lib = lib

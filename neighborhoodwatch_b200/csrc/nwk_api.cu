@@ -26,6 +26,9 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
 int synth_fill(float* out, long long rows, int d, unsigned long long seed, long long row0, int normalize,
                cudaStream_t s);
 
+int validate_pairs(const float* base, long long nb, const float* query, long long nq, int d, const long long* idx,
+                   const float* dist, int k, double rtol, double atol, long long* out_host, cudaStream_t s);
+
 std::atomic<long long> g_launches{0};
 
 std::string& last_error_ref() {
@@ -371,6 +374,19 @@ int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t r
   if (!out || rows < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad synth arguments");
   NWK_TRY(device_check());
   return synth_fill(out, rows, d, seed, row0, normalize, static_cast<cudaStream_t>(stream));
+}
+
+int nwk_validate_pairs(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, const int64_t* idx,
+                       const float* dist, int32_t k, double rtol, double atol, int64_t* mismatches_host,
+                       void* stream) {
+  if (!base || !query || !idx || !dist || !mismatches_host) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (nb <= 0 || nq < 0 || d <= 0 || k <= 0) return fail(NWK_ERR_ARG, "bad shape");
+  NWK_TRY(device_check());
+  long long out = 0;
+  NWK_TRY(validate_pairs(base, nb, query, nq, d, (const long long*)idx, dist, k, rtol, atol, &out,
+                         static_cast<cudaStream_t>(stream)));
+  *mismatches_host = out;
+  return NWK_OK;
 }
 
 int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int64_t b0,

@@ -384,4 +384,64 @@ int merge_topk(int P, const float* dist, const long long* idx, long long nq, int
   return NWK_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// post-validator: the reference's acceptance rule for every returned pair
+// (parquet_to_format.py:351-383: isclose(1 - dot(q, base[idx]), distance / 2)), one warp per pair.
+// HBM gather bound: Q*k rows of 4d bytes.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+validate_pairs_kernel(const float* __restrict__ base, long long nb, const float* __restrict__ query, long long nq,
+                      int d, const long long* __restrict__ idx, const float* __restrict__ dist, int k,
+                      double rtol, double atol, unsigned long long* __restrict__ mismatches) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pairs = nq * k;
+  unsigned long long bad = 0;
+  for (long long pidx = (long long)blockIdx.x * 8 + warp; pidx < pairs; pidx += (long long)gridDim.x * 8) {
+    const long long q = pidx / k;
+    const long long row = idx[pidx];
+    double acc = 0.0;
+    bool nonzero = false;
+    if (row >= 0 && row < nb) {
+      const float* qrow = query + q * d;
+      const float* brow = base + row * d;
+      for (int c = lane; c < d; c += 32) {
+        const float qv = __ldg(qrow + c);
+        nonzero |= (qv != 0.f);
+        acc = fma((double)qv, (double)__ldg(brow + c), acc);
+      }
+    }
+    acc = warp_sum(acc);
+    nonzero = __any_sync(0xffffffffu, nonzero);
+    if (lane == 0) {
+      // zero query vectors are skipped by the reference (parquet_to_format.py:363-366)
+      if (row < 0 || row >= nb) bad += 1;
+      else if (nonzero) {
+        const double a = 1.0 - acc, b = (double)dist[pidx] / 2.0;
+        if (!(fabs(a - b) <= atol + rtol * fabs(b))) bad += 1;      // numpy.isclose(a, b)
+      }
+    }
+  }
+  if (lane == 0 && bad) atomicAdd(mismatches, bad);
+}
+
+int validate_pairs(const float* base, long long nb, const float* query, long long nq, int d, const long long* idx,
+                   const float* dist, int k, double rtol, double atol, long long* out_host, cudaStream_t s) {
+  unsigned long long* dcount = nullptr;
+  NWK_CUDA(cudaMalloc(&dcount, 8));
+  NWK_CUDA(cudaMemsetAsync(dcount, 0, 8, s));
+  long long blocks = (nq * k + 7) / 8;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  validate_pairs_kernel<<<(unsigned)blocks, 256, 0, s>>>(base, nb, query, nq, d, idx, dist, k, rtol, atol, dcount);
+  count_launch();
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, dcount, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(dcount);
+  if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "validate_pairs failed: %s", cudaGetErrorString(e));
+  *out_host = (long long)h;
+  return NWK_OK;
+}
+
 }  // namespace nwk

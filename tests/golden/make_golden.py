@@ -203,6 +203,31 @@ def golden_merge_random(name, P, nq, k, seed, ties):
         print(name, "distinct:", m["distinct"])
 
 
+def golden_fvec_ivec(name):
+    """Bytes written by the reference's own per-row writer (parquet_to_format.py:71-89)."""
+    from neighborhoodwatch import parquet_to_format as ref_fmt
+    rng = np.random.default_rng(7)
+    vec = rng.random((23, 12)).astype(np.float32)
+    idx = rng.integers(0, 2 ** 31 - 1, size=(23, 10), dtype=np.int64)
+    dist = np.sort(rng.random((23, 10)).astype(np.float32), axis=1)
+    with tempfile.TemporaryDirectory() as data_dir:
+        out = {"kind": "fvec_ivec", "vectors": vec, "indices": idx, "distances": dist}
+        ref_fmt.write_ivec_fvec_from_dataframe(data_dir, "m", "v.fvec", pd.DataFrame(vec), "f", 12)
+        ref_fmt.write_ivec_fvec_from_dataframe(data_dir, "m", "i.ivec", pd.DataFrame(idx), "i", 10)
+        ref_fmt.write_ivec_fvec_from_dataframe(data_dir, "m", "d.fvec", pd.DataFrame(dist), "f", 10)
+        # a frame with a trailing RowNum column is trimmed by the reference (:79-80)
+        with_rownum = pd.DataFrame(idx)
+        with_rownum["RowNum"] = np.arange(len(idx))
+        ref_fmt.write_ivec_fvec_from_dataframe(data_dir, "m", "r.ivec", with_rownum, "i", 10)
+        for fn in ("v.fvec", "i.ivec", "d.fvec", "r.ivec"):
+            out[fn.replace(".", "_")] = np.frombuffer(open(os.path.join(data_dir, fn), "rb").read(), dtype=np.uint8)
+        out["count_v"] = ref_fmt.count_vectors(data_dir, "v.fvec")
+        out["nth_v_5"] = np.array(ref_fmt.get_nth_vector(data_dir, "v.fvec", 5), dtype=np.float32)
+        out["nth_i_7"] = np.array(ref_fmt.get_nth_vector(data_dir, "i.ivec", 7), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, "ok")
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REFERENCE), "run this in the build container: /root/reference is not mounted here"
     _install_shims()
@@ -212,3 +237,4 @@ if __name__ == "__main__":
     golden_process_batches("pb_torch_nosplit", nb=700, nq=37, d=128, k=100, batch_size=250, split=False)
     golden_merge_random("merge_random_p5", P=5, nq=40, k=100, seed=1, ties=False)
     golden_merge_random("merge_ties_p3", P=3, nq=20, k=10, seed=2, ties=True)
+    golden_fvec_ivec("fvec_ivec_writer")

@@ -265,3 +265,58 @@ def test_large_shape_properties(cuda_device):
     assert bool(torch.all(~diff | left | right))
     assert float(diff.float().mean()) < 5e-3
     print(st)
+
+
+def test_post_validator_reference_rule(cuda_device):
+    """parquet_to_format.py:351-383: isclose(1 - dot, distance / 2) for every returned pair."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    from neighborhoodwatch_b200 import parquet_to_format as fmt
+    base = synth.vectors(20000, 128, 1234)
+    q = synth.vectors(200, 128, 5678)
+    q[7] = 0.0                                            # zero query vectors are skipped by the reference
+    bd, qd = _dev(base, cuda_device), _dev(q, cuda_device)
+    d, i = knn.knn(bd, qd, 100, metric="sqeuclidean")
+    assert fmt.validate_pairs(bd, qd, i, d) == 0
+    # the same check on the host for a few pairs, as the reference does it
+    dn, inn = d.cpu().numpy(), i.cpu().numpy()
+    for r in (0, 3, 199):
+        for c in (0, 50, 99):
+            dot = float(np.dot(q[r].astype(np.float64), base[inn[r, c]].astype(np.float64)))
+            assert np.isclose(1 - dot, dn[r, c] / 2)
+    bad = d.clone()
+    bad[3, 5] *= 1.01
+    bad[9, 0] += 1e-3
+    assert fmt.validate_pairs(bd, qd, i, bad) == 2
+    wrong = i.clone()
+    wrong[11, 2] = (wrong[11, 2] + 1) % 20000
+    assert fmt.validate_pairs(bd, qd, wrong, d) == 1
+
+
+def test_config2_full_size(cuda_device):
+    """BASELINE config 2 at full size (10 000 x 1 000 000 x 768, cosine, k=100): sampled queries
+    against the on-device fp64 scan, the reference's validator rule on the squared-L2 twin, and
+    size-independent properties."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    from neighborhoodwatch_b200 import parquet_to_format as fmt
+    nq, nb, d, k = 10_000, 1_000_000, 768, 100
+    bd = synth.device_vectors(nb, d, synth.BASE_SEED, device=cuda_device)
+    qd = synth.device_vectors(nq, d, synth.QUERY_SEED, device=cuda_device)
+    got_d, got_i = knn.knn(bd, qd, k, metric="cosine")
+    st = dict(knn.last_stats)
+    assert st["path"] == 1 and st["max_err_ratio"] <= 1.0, st
+    assert st["n_fallback_queries"] <= 10, st
+    assert torch.all(got_d[:, 1:] >= got_d[:, :-1])
+    assert int(got_i.min()) >= 0 and int(got_i.max()) < nb
+    srt = torch.sort(got_i, dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1])
+    sel = torch.arange(0, nq, 157, device=cuda_device)[:64]
+    ex_d, ex_i = knn.knn(bd, qd[sel], k, metric="cosine", force_exact_scan=True)
+    assert torch.equal(ex_i, got_i[sel]) and torch.equal(ex_d, got_d[sel])
+    # unit vectors: cosine ranking == squared-L2 ranking, and the reference's validator rule holds
+    l2_d, l2_i = knn.knn(bd, qd[:2000], k, metric="sqeuclidean")
+    assert fmt.validate_pairs(bd, qd[:2000], l2_i, l2_d) == 0
+    agree = (l2_i == got_i[:2000]).float().mean()
+    assert float(agree) > 0.999        # identical up to fp64-level ties between the two formulas
+    print(st)

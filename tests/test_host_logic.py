@@ -115,6 +115,30 @@ def test_merge_file_count(tmp_path):
     assert merge.get_file_count(str(p)) == 2 == mo.file_count(str(p))
 
 
+def test_fvec_ivec_writer_is_byte_identical_to_the_reference(tmp_path):
+    """Golden bytes come from the reference's own per-row writer (tests/golden/make_golden.py)."""
+    import pandas as pd
+
+    from neighborhoodwatch_b200 import parquet_to_format as fmt
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fvec_ivec_writer.npz"))
+    d = str(tmp_path)
+    fmt.write_ivec_fvec_from_dataframe(d, "m", "v.fvec", pd.DataFrame(g["vectors"]), "f", 12)
+    fmt.write_ivec_fvec_from_dataframe(d, "m", "i.ivec", g["indices"], "i", 10)              # arrays work too
+    fmt.write_ivec_fvec_from_dataframe(d, "m", "d.fvec", pd.DataFrame(g["distances"]), "f", 10)
+    with_rownum = pd.DataFrame(g["indices"])
+    with_rownum["RowNum"] = np.arange(len(with_rownum))
+    fmt.write_ivec_fvec_from_dataframe(d, "m", "r.ivec", with_rownum, "i", 10)
+    for fn in ("v.fvec", "i.ivec", "d.fvec", "r.ivec"):
+        got = np.frombuffer(open(os.path.join(d, fn), "rb").read(), dtype=np.uint8)
+        np.testing.assert_array_equal(got, g[fn.replace(".", "_")], err_msg=fn)
+    assert fmt.count_vectors(d, "v.fvec") == int(g["count_v"]) == 23
+    np.testing.assert_array_equal(np.array(fmt.get_nth_vector(d, "v.fvec", 5), dtype=np.float32), g["nth_v_5"])
+    np.testing.assert_array_equal(np.array(fmt.get_nth_vector(d, "i.ivec", 7), dtype=np.int64), g["nth_i_7"])
+    np.testing.assert_array_equal(fmt.read_vec_file(d, "d.fvec"), g["distances"])
+    with pytest.raises(AssertionError):
+        fmt.write_ivec_fvec_from_dataframe(d, "m", "x.fvec", g["vectors"], "f", 9)
+
+
 def test_shard_bounds_cover_exactly():
     for total, world in [(10, 3), (10 ** 7, 8), (5, 8), (0, 2)]:
         spans = [nwdist.shard_bounds(total, world, r) for r in range(world)]
