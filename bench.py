@@ -117,6 +117,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def gpu_local_cpus(torch, dev_index):
+    """CPUs on the NUMA node the GPU hangs off (sysfs local_cpulist), or None."""
+    try:
+        props = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:  # noqa: BLE001 -- best effort
+        return None
+
+
 def cpu_reference_run(q_count, b_rows, d, k, metric, steps, warmup, budget_rows=None):
     """The reference's CPU-equivalent exact brute force (numpy sgemm + argpartition), all host cores."""
     import numpy as np
@@ -256,7 +277,15 @@ def main():
 
     # ---- end to end through the host-buffer entry point -------------------------------------
     e2e = None
+    numa = None
     if not args.no_e2e:
+        # first-touch the pinned staging buffers from the GPU-local NUMA node: host->device copies
+        # from the far socket run at roughly half the PCIe rate
+        all_cpus = os.sched_getaffinity(0)
+        local = gpu_local_cpus(torch, local_rank)
+        if local:
+            os.sched_setaffinity(0, local)
+            numa = {"gpu_local_cpus": len(local), "of": len(all_cpus)}
         base_host = torch.empty((nb_local, d), dtype=torch.float32, pin_memory=True)
         q_host = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
         base_host.copy_(base)
@@ -297,8 +326,11 @@ def main():
                "ms_per_step": 1e3 * float(t_e2e.item()) / args.e2e_steps,
                "api": "nwk_knn_host_f32 (pinned host base+queries in, host results out; slabs double-buffered)",
                "matches_resident_result": same, "distances_identical": same_d,
-               "rows_with_identical_id_sets": rows_same}
+               "rows_with_identical_id_sets": rows_same, "numa": numa,
+               "h2d_gb_per_s": (nb_local * d * 4 + nq * d * 4) * args.e2e_steps / float(t_e2e.item()) / 1e9}
         del base_host
+        if local:
+            os.sched_setaffinity(0, all_cpus)
 
     if rank != 0:
         if distributed:

@@ -320,3 +320,22 @@ def test_config2_full_size(cuda_device):
     agree = (l2_i == got_i[:2000]).float().mean()
     assert float(agree) > 0.999        # identical up to fp64-level ties between the two formulas
     print(st)
+
+
+def test_clustered_base_sorted_by_cluster(cuda_device):
+    """Real embedding sets are clustered and often stored cluster by cluster: the strided sample
+    must still give usable thresholds, and whatever falls back must stay exact."""
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(11)
+    d, n_clusters, per = 96, 40, 1500
+    centers = rng.standard_normal((n_clusters, d)).astype(np.float32)
+    base = np.concatenate([c + 0.05 * rng.standard_normal((per, d)).astype(np.float32) for c in centers])
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    q = centers[rng.integers(0, n_clusters, 300)] + 0.05 * rng.standard_normal((300, d)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    for metric in ("sqeuclidean", "cosine"):
+        got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric=metric)
+        st = dict(knn.last_stats)
+        _check(got_d, got_i, base, q, 100, metric)
+        assert st["path"] == 1 and st["max_err_ratio"] <= 1.0
+        print(metric, st)
