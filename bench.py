@@ -58,7 +58,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons during the timed region, polled through NVML every
+    few milliseconds (the timed region of a short run is shorter than nvidia-smi's loop period);
+    falls back to `nvidia-smi -lms` (the recipe in B200_PROFILING.md) when pynvml is missing."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,8 +70,28 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.thread = None
+        self.samples = []          # (sm_mhz, power_w, reasons bitmask)
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.sm_max = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical order; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 -- fall back to the CLI
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -80,11 +102,44 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, pw, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [s[0] for s in self.samples]
+            power = [s[1] for s in self.samples]
+            reasons = sorted(n for n, bit in names.items() if any(s[2] & bit for s in self.samples))
+            loaded = sm
+            if power:
+                cut = statistics.median(power)
+                loaded = [c for c, pw in zip(sm, power) if pw >= cut] or sm
+            return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -114,7 +169,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(loaded) if loaded else None,
                 "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def gpu_local_cpus(torch, dev_index):

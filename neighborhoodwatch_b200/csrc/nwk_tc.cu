@@ -8,9 +8,10 @@
 //                    distance (|b|^2 - 2 q.b, -q.b/|b|, -q.b); fp16 copy of the row with a
 //                    per-row power-of-two scale (folded into beta_j).  HBM-bound: reads
 //                    B*d*4 bytes, writes B*d*2.
-//   tc_kernel<SAMPLE>  tcgen05 GEMM of every query tile against a strided sample of base
-//                    tiles; the epilogue keeps the 32 smallest keys per query in registers
-//                    -> threshold tau_q with about `target` rows of the whole base below it.
+//   tc_kernel<SAMPLE>  tcgen05 GEMM of every query tile against a stratified row sample of the base
+//                    (one pseudo-random row per block of 32, gathered by baseprep into a compact
+//                    matrix); the epilogue keeps the 32 smallest keys per query in registers
+//                    -> threshold tau_q with about 1024 rows of the whole base below it.
 //   tc_kernel<FILTER>  the same GEMM over the whole base; the epilogue compares each key with
 //                    tau_q straight out of TMEM and appends the (rare) survivors to a
 //                    per-query candidate log.  The distance matrix never reaches HBM.
@@ -94,8 +95,8 @@ struct TcParams {
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
-  int nS, sChunks, sParts;  // SAMPLE: sample tiles, 32-column chunks used per tile, parts per query tile (1 or 2)
-  const float* alpha;       // [nT*TB]
+  int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (1 or 2)
+  const float* alpha;       // [nT*TB]   (SAMPLE mode: the sample rows' values, [nS*TB])
   const float* beta;        // [nT*TB]
   float* tau;               // [nQT*TQ]
   float* slist;             // SAMPLE: [nq][2][SAMPLE_M] smallest keys per query and sample half
@@ -165,12 +166,41 @@ __device__ __forceinline__ float pow2f(int e) {
 // one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale.
 // The row is read once: up to ROW_CACHE float4 per lane stay in registers between the
 // norm / max pass and the conversion pass (d <= 1024); longer rows re-read their tail (L1/L2).
+// Stratified row sample: block i of `stride` consecutive rows contributes the row
+// i*stride + hash(i) % (rows in the block).  One pseudo-random row per block keeps the sample
+// representative for bases stored cluster by cluster (a tile-granular sample is not).
+__host__ __device__ __forceinline__ long long sample_pick(long long blk, long long stride, long long nb) {
+  unsigned long long z = (unsigned long long)blk * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const long long lo = blk * stride;
+  const long long len = (nb - lo) < stride ? (nb - lo) : stride;
+  return lo + (long long)(z % (unsigned long long)len);
+}
+
+struct SampleOut {
+  long long stride;         // 0 = no sample wanted
+  long long ns, ns_pad;     // sample rows, padded to whole tiles
+  void* rows;               // [ns, dh] fp16 (F16) or [ns, d] fp32 (TF32): the operand copy of the sampled rows
+  float* alpha;             // [ns_pad]
+  float* beta;              // [ns_pad]
+};
+
 template <bool F16>
 __global__ void __launch_bounds__(256)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
-                __half* __restrict__ bh) {
+                __half* __restrict__ bh, const SampleOut so) {
   constexpr int ROW_CACHE = 8;
+  if (so.stride > 0) {
+    const float PINF = __int_as_float(0x7f800000);
+    for (long long i = so.ns + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < so.ns_pad;
+         i += (long long)gridDim.x * blockDim.x) {
+      so.alpha[i] = PINF;
+      so.beta[i] = 0.f;
+    }
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float INF = __int_as_float(0x7f800000);
   const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
@@ -208,6 +238,22 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     }
     a = warp_sum(a);
     int sb = 0;
+    // is this row its block's sample row?
+    long long srow = -1;
+    if (so.stride > 0) {
+      const long long blk = row / so.stride;
+      if (sample_pick(blk, so.stride, nb) == row) srow = blk;
+    }
+    if (!F16 && srow >= 0) {
+      float* frow = reinterpret_cast<float*>(so.rows) + srow * d;
+#pragma unroll
+      for (int i = 0; i < ROW_CACHE; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < d) *reinterpret_cast<float4*>(frow + c) = cache[i];
+      }
+      for (int c = lane * 4 + ROW_CACHE * 128; c < d; c += 128)
+        *reinterpret_cast<float4*>(frow + c) = __ldg(reinterpret_cast<const float4*>(brow + c));
+    }
     if (F16) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -215,6 +261,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       sb = f16_scale_exp(mx);
       const float scale = pow2f(sb);         // exact power of two: v * scale is exact up to fp16 rounding
       __half* hrow = bh + row * dh;
+      __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * dh : nullptr;
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
         const int c = lane * 4 + i * 128;
@@ -226,6 +273,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
           pk.x = *reinterpret_cast<unsigned int*>(&h01);
           pk.y = *reinterpret_cast<unsigned int*>(&h23);
           *reinterpret_cast<uint2*>(hrow + c) = pk;
+          if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
         }
       }
       for (int c = lane * 4 + ROW_CACHE * 128; c < dh; c += 128) {
@@ -237,6 +285,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         pk.x = *reinterpret_cast<unsigned int*>(&h01);
         pk.y = *reinterpret_cast<unsigned int*>(&h23);
         *reinterpret_cast<uint2*>(hrow + c) = pk;
+        if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
       }
     }
     if (lane == 0) {
@@ -249,6 +298,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       }
       alpha[row] = al;
       beta[row] = be;
+      if (srow >= 0) { so.alpha[srow] = al; so.beta[srow] = be; }
       local_max = fmaxf(local_max, __double2float_ru(a));
     }
   }
@@ -346,7 +396,7 @@ struct Sched {
     }
     out_qt = qt;
     if (MODE == MODE_FILTER) out_t = c * G + i;
-    else if (MODE == MODE_SAMPLE) out_t = (int)(((long long)(c + i) * nT) / nS);
+    else if (MODE == MODE_SAMPLE) out_t = c + i;
     else out_t = dump_t;
     first = (i == 0);
     last = (i == len - 1);
@@ -928,6 +978,7 @@ struct TcPlan {
   int nQT, nT, nKB, G, nChunks, nUnits, nS, sChunks, sParts, dh;
   bool sample;
   long long nb_pad, nq_pad;
+  long long s_stride, ns, ns_pad;
 };
 
 static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16) {
@@ -948,18 +999,13 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
   // sampling only pays when the base is larger than what the log can simply hold
   pl.sample = nb > LOG_CAP / 2;
   if (pl.sample) {
-    // the SAMPLE_M-th smallest key of n_s sampled rows has about SAMPLE_M * nb / n_s rows of
-    // the whole base below it: n_s = SAMPLE_M * nb / LOG_TARGET
-    long long ns_rows = ((long long)SAMPLE_M * nb + LOG_TARGET - 1) / LOG_TARGET;
-    if (ns_rows < SAMPLE_M * 2) ns_rows = SAMPLE_M * 2;
-    long long cols;      // columns used per sample tile: spread small samples over >= 16 tiles
-    if (ns_rows >= 16 * TB) cols = TB;
-    else { cols = (ns_rows / 16 + 31) / 32 * 32; if (cols < 32) cols = 32; }
-    long long ns = (ns_rows + cols - 1) / cols;
-    if (ns > pl.nT) ns = pl.nT;
-    if (ns < 1) ns = 1;
-    pl.nS = (int)ns;
-    pl.sChunks = (int)(cols / 32);
+    // the SAMPLE_M-th smallest key of a sample of every `stride`-th row has about
+    // SAMPLE_M * stride rows of the whole base below it
+    pl.s_stride = LOG_TARGET / SAMPLE_M;
+    pl.ns = (nb + pl.s_stride - 1) / pl.s_stride;
+    pl.ns_pad = (pl.ns + TB - 1) / TB * TB;
+    pl.nS = (int)(pl.ns_pad / TB);
+    pl.sChunks = TB / 32;
     pl.sParts = (2 * pl.nQT <= sms && pl.nS >= 2) ? 2 : 1;
   }
   return pl;
@@ -977,6 +1023,8 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)nq * 2 * SAMPLE_M * 4, 256);    // half-sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
   bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
+  bytes += align_up((size_t)pl.ns_pad * 4, 256) * 2;        // sample alpha, beta
+  bytes += align_up((size_t)(pl.ns + 1) * (size_t)(d > pl.dh ? d : pl.dh) * 4, 256);   // sample rows (fp16 or fp32)
   bytes += 4096;                                            // scalars
   // fallback scan for up to 64 queries is always provisioned; more is handled in rounds
   bytes += exact_scan_workspace_bytes(nb, 64, k) + 256;
@@ -1013,6 +1061,9 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   float* slist = ar.take<float>((size_t)nq * 2 * SAMPLE_M);
   __half* bh = ar.take<__half>((size_t)nb * pl.dh);
   __half* qh = ar.take<__half>((size_t)nq * pl.dh);
+  float* salpha = ar.take<float>((size_t)pl.ns_pad);
+  float* sbeta = ar.take<float>((size_t)pl.ns_pad);
+  float* srows = ar.take<float>((size_t)(pl.ns + 1) * (size_t)(d > pl.dh ? d : pl.dh));
   Scalars* sc = ar.take<Scalars>(1);
   ar.off = align_up(ar.off, 256);
   void* scan_ws = ar.base + ar.off;
@@ -1038,8 +1089,13 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   {
     long long blocks = (pl.nb_pad + 7) / 8;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh);
-    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh);
+    SampleOut so{};
+    if (pl.sample) {
+      so.stride = pl.s_stride; so.ns = pl.ns; so.ns_pad = pl.ns_pad;
+      so.rows = srows; so.alpha = salpha; so.beta = sbeta;
+    }
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[1], s);
@@ -1061,8 +1117,14 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (pl.sample) {
     fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * 2 * SAMPLE_M, HUGE_VALF);
     NWK_LAUNCH_CHECK();
+    // the sample pass scans the compact matrix of sampled rows with their own alpha / beta
+    CUtensorMap tm_s;
+    if (f16) NWK_TRY(make_tmap(&tm_s, srows, pl.ns, pl.dh, true, TB));
+    else NWK_TRY(make_tmap(&tm_s, srows, pl.ns, d, false, TB));
+    TcParams ps = p;
+    ps.alpha = salpha; ps.beta = sbeta; ps.nT = pl.nS;
     int grid = pl.sParts * pl.nQT < sms ? pl.sParts * pl.nQT : sms;
-    NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_b, p, s));
+    NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s));
     tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, tau);
     NWK_LAUNCH_CHECK();
   } else {
@@ -1186,12 +1248,12 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_LAUNCH_CHECK();
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh);
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, SampleOut{});
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh);
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, SampleOut{});
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);
