@@ -66,6 +66,7 @@ constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + M
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
+static_assert(((LOG_TARGET / SAMPLE_M) & (LOG_TARGET / SAMPLE_M - 1)) == 0, "sample stride must be a power of two");
 constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
 constexpr int TC_MAX_K = 256;
 #ifndef NWK_SLOW_BATCH
@@ -169,18 +170,19 @@ __device__ __forceinline__ float pow2f(int e) {
 // Stratified row sample: block i of `stride` consecutive rows contributes the row
 // i*stride + hash(i) % (rows in the block).  One pseudo-random row per block keeps the sample
 // representative for bases stored cluster by cluster (a tile-granular sample is not).
-__host__ __device__ __forceinline__ long long sample_pick(long long blk, long long stride, long long nb) {
+__host__ __device__ __forceinline__ long long sample_pick(long long blk, int stride_log2, long long nb) {
   unsigned long long z = (unsigned long long)blk * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
-  const long long lo = blk * stride;
-  const long long len = (nb - lo) < stride ? (nb - lo) : stride;
-  return lo + (long long)(z % (unsigned long long)len);
+  const long long lo = blk << stride_log2;
+  long long pick = lo + (long long)(z & ((1ull << stride_log2) - 1));
+  if (pick >= nb) pick = lo + (long long)(z % (unsigned long long)(nb - lo));   // short last block
+  return pick;
 }
 
 struct SampleOut {
-  long long stride;         // 0 = no sample wanted
+  int stride_log2;          // rows per block = 2^stride_log2; < 0 = no sample wanted
   long long ns, ns_pad;     // sample rows, padded to whole tiles
   void* rows;               // [ns, dh] fp16 (F16) or [ns, d] fp32 (TF32): the operand copy of the sampled rows
   float* alpha;             // [ns_pad]
@@ -193,7 +195,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
                 __half* __restrict__ bh, const SampleOut so) {
   constexpr int ROW_CACHE = 8;
-  if (so.stride > 0) {
+  if (so.stride_log2 >= 0) {
     const float PINF = __int_as_float(0x7f800000);
     for (long long i = so.ns + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < so.ns_pad;
          i += (long long)gridDim.x * blockDim.x) {
@@ -240,9 +242,9 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     int sb = 0;
     // is this row its block's sample row?
     long long srow = -1;
-    if (so.stride > 0) {
-      const long long blk = row / so.stride;
-      if (sample_pick(blk, so.stride, nb) == row) srow = blk;
+    if (so.stride_log2 >= 0) {
+      const long long blk = row >> so.stride_log2;
+      if (sample_pick(blk, so.stride_log2, nb) == row) srow = blk;
     }
     if (!F16 && srow >= 0) {
       float* frow = reinterpret_cast<float*>(so.rows) + srow * d;
@@ -1090,8 +1092,11 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     long long blocks = (pl.nb_pad + 7) / 8;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     SampleOut so{};
+    so.stride_log2 = -1;
     if (pl.sample) {
-      so.stride = pl.s_stride; so.ns = pl.ns; so.ns_pad = pl.ns_pad;
+      so.stride_log2 = 0;
+      while ((1ll << so.stride_log2) < pl.s_stride) ++so.stride_log2;     // LOG_TARGET / SAMPLE_M is a power of two
+      so.ns = pl.ns; so.ns_pad = pl.ns_pad;
       so.rows = srows; so.alpha = salpha; so.beta = sbeta;
     }
     if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
@@ -1241,6 +1246,8 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
   NWK_CUDA(cudaMalloc(&beta, pl.nb_pad * 4));
   CUtensorMap tm_q, tm_b;
   int rc = NWK_OK;
+  SampleOut no_sample{};
+  no_sample.stride_log2 = -1;
   if (f16) {
     NWK_CUDA(cudaMalloc(&bh, (size_t)nb * pl.dh * 2));
     NWK_CUDA(cudaMalloc(&qh, (size_t)nq * pl.dh * 2));
@@ -1248,12 +1255,12 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_LAUNCH_CHECK();
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, SampleOut{});
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, SampleOut{});
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);
