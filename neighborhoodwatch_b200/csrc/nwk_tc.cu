@@ -807,7 +807,7 @@ select_kernel(const FinParams p) {
 }
 
 // rerank: fp64 distance of every kept row, RR_ROWS rows in flight per warp (HBM gather bound)
-__global__ void __launch_bounds__(RR_THREADS)
+__global__ void __launch_bounds__(RR_THREADS, 4)
 rerank_kernel(const FinParams p) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   float* s_q = reinterpret_cast<float*>(rr_smem);                                           // [d]
