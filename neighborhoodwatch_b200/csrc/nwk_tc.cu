@@ -67,7 +67,8 @@ constexpr int SAMPLE_M = 32;                   // per-query sample list length (
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
 static_assert(((LOG_TARGET / SAMPLE_M) & (LOG_TARGET / SAMPLE_M - 1)) == 0, "sample stride must be a power of two");
-constexpr int RERANK_MAX = 1024;               // most rows re-ranked in fp64 per query
+constexpr int RERANK_MAX = 2048;               // most rows re-ranked in fp64 per query (fp64 results live in log slots [LOG_CAP/2, LOG_CAP))
+static_assert(RERANK_MAX <= LOG_CAP / 2, "re-ranked distances alias the upper half of the query's log");
 constexpr int TC_MAX_K = 256;
 #ifndef NWK_SLOW_BATCH
 #define NWK_SLOW_BATCH 1          // hit columns whose TMEM loads are in flight together (1 = one at a time)
