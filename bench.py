@@ -295,8 +295,24 @@ def main():
         agg["rerank"] += st["total_rerank"]
         return out
 
+    exch_events = []
+
+    def merge_timed(all_d, all_i, kk):
+        out = knn.merge_topk(all_d, all_i, kk)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        exch_events[-1].append(e)
+        return out
+
+    def local_knn_timed(b, q, kk, m, off):
+        out = local_knn(b, q, kk, m, off)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()                       # local top-k done; what follows is all-gather + merge
+        exch_events.append([e])
+        return out
+
     def step():
-        return nwdist.sharded_knn(base, queries, k, metric, lo, local_knn=local_knn, merge=knn.merge_topk)
+        return nwdist.sharded_knn(base, queries, k, metric, lo, local_knn=local_knn_timed, merge=merge_timed)
 
     def barrier():
         if distributed:
@@ -309,6 +325,7 @@ def main():
         v.clear()
     for key in agg:
         agg[key] = 0
+    exch_events.clear()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -397,6 +414,11 @@ def main():
         if local:
             os.sched_setaffinity(0, all_cpus)
 
+    exchange_ms = None
+    if distributed:
+        pairs_ev = [ev for ev in exch_events if len(ev) == 2]
+        if pairs_ev:
+            exchange_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs_ev)
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -427,6 +449,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands -> f32 accumulate (candidates) + f64 (rerank)",
             "data": "synthetic", "config": config, "queries_per_s": nq * args.steps / elapsed_s,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_t.item()), "roofline": roofline,
+            "exchange_ms_per_step": exchange_ms,   # all-gather of the [Q,k] lists + merge kernel (rank 0), N > 1 only
             "exactness": {"fallback_queries_per_step": agg["fallback"] / max(args.steps, 1),
                           "mean_candidates_per_query": agg["cand"] / max(args.steps * nq, 1),
                           "mean_rerank_per_query": agg["rerank"] / max(args.steps * nq, 1),
