@@ -16,8 +16,8 @@
 //                    tau_q straight out of TMEM and appends the (rare) survivors to a
 //                    per-query candidate log.  The distance matrix never reaches HBM.
 //                    Tensor-pipe / L2 bound: 2*Q*B*d FLOP.
-//   select_kernel    per query: sort the log, keep every candidate whose approximate key lies
-//                    within 2*eps of the k-th (eps = proven error bound of the fp16 operands).
+//   select_kernel    per query: radix-select the k-th smallest logged key, keep every candidate
+//                    within 2*eps of it (eps = proven error bound of the fp16 operands).
 //                    A query is *certified* when tau_q lies above that band (no row outside the
 //                    log can belong to the true top-k); the rest go to the fp64 scan.
 //   rerank_kernel    recompute the kept rows in fp64 from the fp32 inputs (HBM gather bound).
@@ -725,22 +725,26 @@ constexpr int RR_ROWS = 4;                       // candidate rows in flight per
 constexpr int RR_BLOCK_ROWS = (RR_THREADS / 32) * RR_ROWS;
 constexpr int OUT_THREADS = 128;
 
-// select: sort the query's log, find the band [a_k, a_k + 2 eps], certify, keep the R rows in it
+// select: find the k-th smallest logged key a_k by radix select (4 passes of 8 bits over the
+// order-preserving 32-bit keys), form the band [a_k, a_k + 2 eps], certify, and compact the R
+// records inside the band to the front of the query's log (order is irrelevant: output_kernel
+// sorts by exact distance).  Shared-memory histogram work only; ~4x cheaper than sorting the log.
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const FinParams p) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   unsigned long long* s_log = reinterpret_cast<unsigned long long*>(sel_smem);             // [LOG_CAP]
+  __shared__ unsigned int s_hist[256];
   __shared__ double s_qn2;
-  __shared__ int s_R;
+  __shared__ unsigned int s_prefix, s_kk, s_thr_ord;
+  __shared__ int s_R, s_fail;
 
   const long long q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned int total = p.cnt[q];
   const int c = (int)min(total, (unsigned int)LOG_CAP);
-  const int n2 = max(next_pow2(c), 2);
   unsigned long long* glog = p.log + q * LOG_CAP;
 
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) s_log[i] = (i < c) ? glog[i] : ~0ull;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) s_log[i] = glog[i];
   if (warp == 0) {
     // |q|^2 in the same operation order as scan_dist_kernel
     double a = 0.0;
@@ -749,13 +753,59 @@ select_kernel(const FinParams p) {
     a = warp_sum(a);
     if (lane == 0) s_qn2 = a;
   }
-  block_bitonic_sort_u64(s_log, n2);
+  const bool countable = !(total > (unsigned int)LOG_CAP || c < p.k);
+  if (threadIdx.x == 0) { s_prefix = 0; s_kk = (unsigned int)(p.k - 1); }
+  __syncthreads();
+
+  if (countable) {
+    // radix select of the element of rank k-1 among the c keys
+    unsigned int mask = 0;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned int prefix = s_prefix;
+      for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned int key = (unsigned int)(s_log[i] >> 32);
+        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns bins [8l, 8l+8): inclusive scan across lanes, then locate the digit
+        unsigned int loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = s_hist[lane * 8 + j]; sum += loc[j]; }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const unsigned int excl = incl - sum;
+        const unsigned int kk = s_kk;
+        if (kk >= excl && kk < incl) {           // exactly one lane
+          unsigned int run = excl;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (kk >= run && kk < run + loc[j]) {
+              s_prefix = prefix | ((unsigned int)(lane * 8 + j) << shift);
+              s_kk = kk - run;
+            }
+            run += loc[j];
+          }
+        }
+      }
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+  }
 
   if (threadIdx.x == 0) {
     const double qn2 = s_qn2;
-    int fail = 0, R = 0;
+    int fail = 0;
     double eps = 0.0;
-    if (total > (unsigned int)LOG_CAP || c < p.k) {
+    unsigned int thr_ord = 0;
+    if (!countable) {
       fail = 1;
     } else {
       // proven bound on |approximate key - exact key| for this query (DESIGN.md "error bound")
@@ -773,22 +823,39 @@ select_kernel(const FinParams p) {
       eps = eps_dot;
       if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
       else if (p.metric == NWK_METRIC_COSINE) eps = eps_cos;
-      const float key_k = ord2f((uint32_t)(s_log[p.k - 1] >> 32));
+      const float key_k = ord2f(s_prefix);     // the k-th smallest approximate key
       // + the fp32 rounding of alpha + beta*acc itself
       eps += 3.0e-7 * fabs((double)key_k) + 1e-30;
       const float thr = __double2float_ru((double)key_k + 2.0 * eps);
       const float tau = p.tau[q];
       if (!(thr < tau)) fail = 1;          // band reaches the logging threshold: cannot certify
-      // R = number of logged keys <= thr (log is sorted)
-      const uint32_t thr_ord = f2ord(thr);
-      int lo = p.k, hi = c;                // first index in [k, c) with key > thr
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if ((uint32_t)(s_log[mid] >> 32) <= thr_ord) lo = mid + 1; else hi = mid;
-      }
-      R = lo;
-      if (R > RERANK_MAX) { fail = 1; R = RERANK_MAX; }
+      thr_ord = f2ord(thr);
     }
+    s_fail = fail;
+    s_thr_ord = thr_ord;
+    s_R = 0;
+    p.epsq[q] = (float)eps;
+    p.qn2[q] = qn2;
+  }
+  __syncthreads();
+
+  // compact the records with key <= thr to the front of the query's log
+  int R = 0;
+  if (countable) {
+    const unsigned int thr_ord = s_thr_ord;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      const unsigned long long rec = s_log[i];
+      if ((unsigned int)(rec >> 32) <= thr_ord) {
+        const int pos = atomicAdd(&s_R, 1);
+        if (pos < RERANK_MAX && !s_fail) glog[pos] = rec;
+      }
+    }
+    __syncthreads();
+    R = s_R;
+  }
+  if (threadIdx.x == 0) {
+    int fail = s_fail;
+    if (R > RERANK_MAX) { fail = 1; R = RERANK_MAX; }
     atomicAdd(p.sc->stat_sum + 0, (unsigned long long)total);
     atomicAdd(p.sc->stat_sum + 1, (unsigned long long)R);
     atomicMax(p.sc->stat_max + 0, total);
@@ -798,13 +865,7 @@ select_kernel(const FinParams p) {
       p.fail_list[slot] = (int)q;
     }
     p.rr[q] = fail ? -1 : R;
-    p.epsq[q] = (float)eps;
-    p.qn2[q] = qn2;
-    s_R = fail ? 0 : R;
   }
-  __syncthreads();
-  const int R = s_R;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) glog[i] = s_log[i];
 }
 
 // rerank: fp64 distance of every kept row, RR_ROWS rows in flight per warp (HBM gather bound)
