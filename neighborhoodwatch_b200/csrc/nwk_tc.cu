@@ -408,8 +408,13 @@ struct Sched {
   }
 };
 
+// The filter pass runs 4 control warps + 2 epilogue warpgroups (384 threads); the sample and
+// dump passes use one epilogue warpgroup and are launched with 256 threads, which leaves room on
+// the SM for a block of the concurrently running base preparation.
+template <int MODE> constexpr int tc_threads() { return MODE == MODE_FILTER ? TC_THREADS : 256; }
+
 template <int MODE, bool F16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads<MODE>(), 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
   constexpr int BK = Op<F16>::BK;
@@ -1098,9 +1103,9 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
 template <bool F16>
 static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMap& tb, const TcParams& p,
                      cudaStream_t s) {
-  if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
-  else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
-  else tc_kernel<MODE_DUMP, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, tc_threads<MODE_SAMPLE>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, tc_threads<MODE_FILTER>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else tc_kernel<MODE_DUMP, F16><<<grid, tc_threads<MODE_DUMP>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
   NWK_LAUNCH_CHECK();
   return NWK_OK;
 }
@@ -1183,7 +1188,10 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   NWK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   {
     long long blocks = (pl.nb_pad + 7) / 8;
-    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    // one block per SM while the sample pass shares the SMs (its CTA needs most of the register
+    // file); otherwise enough blocks to saturate HBM
+    const long long per_sm = pl.sample ? 1 : 16;
+    if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;
     if (f16) baseprep_kernel<true, false><<<(unsigned)blocks, 256, 0, side>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
     else baseprep_kernel<false, false><<<(unsigned)blocks, 256, 0, side>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
     NWK_LAUNCH_CHECK();
