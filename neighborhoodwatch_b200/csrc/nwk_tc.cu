@@ -190,30 +190,26 @@ struct SampleOut {
   float* beta;              // [ns_pad]
 };
 
-// SAMPLE_ONLY = false: every base row -> alpha / beta (padded to whole tiles), max norm, fp16 operand copy.
-// SAMPLE_ONLY = true : only the stratified sample rows -> compact sample matrix + its alpha / beta
-//                      (runs first, so the sample pass can overlap the full preparation).
-template <bool F16, bool SAMPLE_ONLY>
+template <bool F16>
 __global__ void __launch_bounds__(256)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
                 __half* __restrict__ bh, const SampleOut so) {
   constexpr int ROW_CACHE = 8;
-  const float INF = __int_as_float(0x7f800000);
-  if (SAMPLE_ONLY) {
+  if (so.stride_log2 >= 0) {
+    const float PINF = __int_as_float(0x7f800000);
     for (long long i = so.ns + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < so.ns_pad;
          i += (long long)gridDim.x * blockDim.x) {
-      so.alpha[i] = INF;
+      so.alpha[i] = PINF;
       so.beta[i] = 0.f;
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
   const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
   float local_max = 0.f;
-  const long long n_iter = SAMPLE_ONLY ? so.ns : nb_pad;
-  for (long long it = (long long)blockIdx.x * 8 + warp; it < n_iter; it += (long long)gridDim.x * 8) {
-    const long long row = SAMPLE_ONLY ? sample_pick(it, so.stride_log2, nb) : it;
-    if (!SAMPLE_ONLY && row >= nb) {
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
+    if (row >= nb) {
       if (lane == 0) { alpha[row] = INF; beta[row] = 0.f; }
       continue;
     }
@@ -245,9 +241,14 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     }
     a = warp_sum(a);
     int sb = 0;
-    if (!F16 && SAMPLE_ONLY) {
-      // TF32 operands are the fp32 values themselves: the sample matrix is a plain copy of the rows
-      float* frow = reinterpret_cast<float*>(so.rows) + it * d;
+    // is this row its block's sample row?
+    long long srow = -1;
+    if (so.stride_log2 >= 0) {
+      const long long blk = row >> so.stride_log2;
+      if (sample_pick(blk, so.stride_log2, nb) == row) srow = blk;
+    }
+    if (!F16 && srow >= 0) {
+      float* frow = reinterpret_cast<float*>(so.rows) + srow * d;
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
         const int c = lane * 4 + i * 128;
@@ -262,7 +263,8 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       if (!(mx < INF)) mx = 0.f;             // inf / nan rows: leave unscaled (they never rank)
       sb = f16_scale_exp(mx);
       const float scale = pow2f(sb);         // exact power of two: v * scale is exact up to fp16 rounding
-      __half* hrow = SAMPLE_ONLY ? reinterpret_cast<__half*>(so.rows) + it * dh : bh + row * dh;
+      __half* hrow = bh + row * dh;
+      __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * dh : nullptr;
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
         const int c = lane * 4 + i * 128;
@@ -274,6 +276,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
           pk.x = *reinterpret_cast<unsigned int*>(&h01);
           pk.y = *reinterpret_cast<unsigned int*>(&h23);
           *reinterpret_cast<uint2*>(hrow + c) = pk;
+          if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
         }
       }
       for (int c = lane * 4 + ROW_CACHE * 128; c < dh; c += 128) {
@@ -285,6 +288,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         pk.x = *reinterpret_cast<unsigned int*>(&h01);
         pk.y = *reinterpret_cast<unsigned int*>(&h23);
         *reinterpret_cast<uint2*>(hrow + c) = pk;
+        if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
       }
     }
     if (lane == 0) {
@@ -295,17 +299,13 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       else if (metric == NWK_METRIC_COSINE) {
         if (a > 0.0) be = (float)(-1.0 / sqrt(a)) * unscale; else { al = INF; be = 0.f; }
       }
-      if (SAMPLE_ONLY) {
-        so.alpha[it] = al;
-        so.beta[it] = be;
-      } else {
-        alpha[row] = al;
-        beta[row] = be;
-        local_max = fmaxf(local_max, __double2float_ru(a));
-      }
+      alpha[row] = al;
+      beta[row] = be;
+      if (srow >= 0) { so.alpha[srow] = al; so.beta[srow] = be; }
+      local_max = fmaxf(local_max, __double2float_ru(a));
     }
   }
-  if (!SAMPLE_ONLY && lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
+  if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
 }
 
 // tau_q = SAMPLE_M-th smallest of the two half-sample lists of query q (one warp per query)
@@ -408,13 +408,8 @@ struct Sched {
   }
 };
 
-// The filter pass runs 4 control warps + 2 epilogue warpgroups (384 threads); the sample and
-// dump passes use one epilogue warpgroup and are launched with 256 threads, which leaves room on
-// the SM for a block of the concurrently running base preparation.
-template <int MODE> constexpr int tc_threads() { return MODE == MODE_FILTER ? TC_THREADS : 256; }
-
 template <int MODE, bool F16>
-__global__ void __launch_bounds__(tc_threads<MODE>(), 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
   constexpr int BK = Op<F16>::BK;
@@ -1103,9 +1098,9 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
 template <bool F16>
 static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMap& tb, const TcParams& p,
                      cudaStream_t s) {
-  if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, tc_threads<MODE_SAMPLE>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
-  else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, tc_threads<MODE_FILTER>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
-  else tc_kernel<MODE_DUMP, F16><<<grid, tc_threads<MODE_DUMP>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
+  if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else tc_kernel<MODE_DUMP, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
   NWK_LAUNCH_CHECK();
   return NWK_OK;
 }
@@ -1155,48 +1150,21 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
     NWK_LAUNCH_CHECK();
   }
-  // The full preparation (HBM bound, every SM lightly loaded) runs on a side stream while the
-  // sample pass (tensor / epilogue bound, one CTA per query tile) runs on the caller's stream;
-  // the sample rows are prepared first by a small gather kernel.  The filter pass joins both.
-  static cudaStream_t side_streams[64] = {};
-  int dev_id = 0;
-  NWK_CUDA(cudaGetDevice(&dev_id));
-  if (dev_id < 0 || dev_id >= 64) return fail(NWK_ERR_DEVICE, "device ordinal %d out of range", dev_id);
-  if (!side_streams[dev_id]) NWK_CUDA(cudaStreamCreateWithFlags(&side_streams[dev_id], cudaStreamNonBlocking));
-  cudaStream_t side = side_streams[dev_id];
-  struct EventPair {            // destroyed on every exit path
-    cudaEvent_t fork = nullptr, join = nullptr;
-    ~EventPair() { if (fork) cudaEventDestroy(fork); if (join) cudaEventDestroy(join); }
-  } evp;
-  NWK_CUDA(cudaEventCreateWithFlags(&evp.fork, cudaEventDisableTiming));
-  NWK_CUDA(cudaEventCreateWithFlags(&evp.join, cudaEventDisableTiming));
-  cudaEvent_t ev_fork = evp.fork, ev_join = evp.join;
-  SampleOut so{};
-  so.stride_log2 = -1;
-  if (pl.sample) {
-    so.stride_log2 = 0;
-    while ((1ll << so.stride_log2) < pl.s_stride) ++so.stride_log2;     // LOG_TARGET / SAMPLE_M is a power of two
-    so.ns = pl.ns; so.ns_pad = pl.ns_pad;
-    so.rows = srows; so.alpha = salpha; so.beta = sbeta;
-    long long sblocks = (pl.ns + 7) / 8;
-    if (sblocks > (long long)sms * 8) sblocks = (long long)sms * 8;
-    if (f16) baseprep_kernel<true, true><<<(unsigned)sblocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
-    else baseprep_kernel<false, true><<<(unsigned)sblocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
-    NWK_LAUNCH_CHECK();
-  }
-  NWK_CUDA(cudaEventRecord(ev_fork, s));
-  NWK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   {
     long long blocks = (pl.nb_pad + 7) / 8;
-    // one block per SM while the sample pass shares the SMs (its CTA needs most of the register
-    // file); otherwise enough blocks to saturate HBM
-    const long long per_sm = pl.sample ? 1 : 16;
-    if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;
-    if (f16) baseprep_kernel<true, false><<<(unsigned)blocks, 256, 0, side>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
-    else baseprep_kernel<false, false><<<(unsigned)blocks, 256, 0, side>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    SampleOut so{};
+    so.stride_log2 = -1;
+    if (pl.sample) {
+      so.stride_log2 = 0;
+      while ((1ll << so.stride_log2) < pl.s_stride) ++so.stride_log2;     // LOG_TARGET / SAMPLE_M is a power of two
+      so.ns = pl.ns; so.ns_pad = pl.ns_pad;
+      so.rows = srows; so.alpha = salpha; so.beta = sbeta;
+    }
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
     NWK_LAUNCH_CHECK();
   }
-  NWK_CUDA(cudaEventRecord(ev_join, side));
   if (profile) cudaEventRecord(ev[1], s);
 
   CUtensorMap tm_q, tm_b;
@@ -1230,7 +1198,6 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
     NWK_LAUNCH_CHECK();
   }
-  NWK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));      // alpha / beta / fp16 base are ready
   if (profile) cudaEventRecord(ev[2], s);
   {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
@@ -1350,12 +1317,12 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_LAUNCH_CHECK();
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true, false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false, false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);
