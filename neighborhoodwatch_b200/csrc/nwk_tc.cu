@@ -64,6 +64,10 @@ constexpr int APPEND_BYTES = APPEND_SLOTS * TQ * EPI_WG_MAX * 8;
 constexpr int MASK_BYTES = (TB / 32) * TQ * 4;           // per-thread hit masks of its column chunks
 constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES + 256 + 1024;
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
+constexpr int SAMPLE_WARM = 4;                 // warm-up: the 4 smallest of a part's first 4 chunks (128 sample rows) set the first threshold
+constexpr int SAMPLE_QCAP = (APPEND_BYTES + MASK_BYTES) / (TQ * 4);   // per-thread queue of admitted keys (shared memory)
+constexpr int SAMPLE_MAX_PARTS = 8;            // parts a query tile's sample scan may be split into
+static_assert(SAMPLE_QCAP >= 40, "the queue must take a whole 32-column chunk beyond the flush mark");
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
 static_assert(((LOG_TARGET / SAMPLE_M) & (LOG_TARGET / SAMPLE_M - 1)) == 0, "sample stride must be a power of two");
@@ -97,11 +101,11 @@ struct TcParams {
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
-  int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (1 or 2)
+  int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (<= SAMPLE_MAX_PARTS)
   const float* alpha;       // [nT*TB]   (SAMPLE mode: the sample rows' values, [nS*TB])
   const float* beta;        // [nT*TB]
   float* tau;               // [nQT*TQ]
-  float* slist;             // SAMPLE: [nq][2][SAMPLE_M] smallest keys per query and sample half
+  float* slist;             // SAMPLE: [nq][sParts][SAMPLE_M] smallest keys per query and sample part
   unsigned int* cnt;        // [nq]
   unsigned long long* log;  // [nq][LOG_CAP]
   float* dump;              // MODE_DUMP: [TQ][TB]
@@ -709,7 +713,8 @@ struct FinParams {
   long long id_offset;
   const float* tau; const unsigned int* cnt;
   unsigned long long* log;     // [nq][LOG_CAP]; select rewrites [0,R) sorted, rerank writes fp64 at [LOG_CAP/2, LOG_CAP/2+R)
-  int* rr;                     // [nq] rows to re-rank, -1 = uncertified
+  int* rr;                     // [nq] rows to re-rank (approximate key <= a_k + eps), -1 = uncertified
+  int* rr2;                    // [nq] rows in the outer band (a_k + eps, a_k + 2 eps], parked at the end of the record half
   float* epsq;                 // [nq] proven key error bound
   double* qn2;                 // [nq] |q|^2
   Scalars* sc;
@@ -735,8 +740,8 @@ select_kernel(const FinParams p) {
   unsigned long long* s_log = reinterpret_cast<unsigned long long*>(sel_smem);             // [LOG_CAP]
   __shared__ unsigned int s_hist[256];
   __shared__ double s_qn2;
-  __shared__ unsigned int s_prefix, s_kk, s_thr_ord;
-  __shared__ int s_R, s_fail;
+  __shared__ unsigned int s_prefix, s_kk, s_thr_ord, s_thr1_ord;
+  __shared__ int s_R, s_R2, s_fail;
 
   const long long q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -804,7 +809,7 @@ select_kernel(const FinParams p) {
     const double qn2 = s_qn2;
     int fail = 0;
     double eps = 0.0;
-    unsigned int thr_ord = 0;
+    unsigned int thr_ord = 0, thr1_ord = 0;
     if (!countable) {
       fail = 1;
     } else {
@@ -830,32 +835,44 @@ select_kernel(const FinParams p) {
       const float tau = p.tau[q];
       if (!(thr < tau)) fail = 1;          // band reaches the logging threshold: cannot certify
       thr_ord = f2ord(thr);
+      thr1_ord = f2ord(__double2float_ru((double)key_k + eps));
     }
     s_fail = fail;
     s_thr_ord = thr_ord;
+    s_thr1_ord = thr1_ord;
     s_R = 0;
+    s_R2 = 0;
     p.epsq[q] = (float)eps;
     p.qn2[q] = qn2;
   }
   __syncthreads();
 
-  // compact the records with key <= thr to the front of the query's log
-  int R = 0;
+  // Compact the records of the inner band (key <= a_k + eps) to the front of the query's log:
+  // rerank_kernel recomputes exactly these.  Their exact k-th distance D_k bounds the true k-th
+  // from above, so a row of the outer band (a_k + eps, a_k + 2 eps] can only matter when its
+  // key is <= D_k + eps; those records are parked at the end of the record half of the log
+  // (slots LOG_CAP/2-1 downwards) and output_kernel re-ranks the few that pass that test.
+  int R = 0, R2 = 0;
   if (countable) {
-    const unsigned int thr_ord = s_thr_ord;
+    const unsigned int thr_ord = s_thr_ord, thr1_ord = s_thr1_ord;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
       const unsigned long long rec = s_log[i];
-      if ((unsigned int)(rec >> 32) <= thr_ord) {
+      const unsigned int o = (unsigned int)(rec >> 32);
+      if (o <= thr1_ord) {
         const int pos = atomicAdd(&s_R, 1);
         if (pos < RERANK_MAX && !s_fail) glog[pos] = rec;
+      } else if (o <= thr_ord) {
+        const int pos = atomicAdd(&s_R2, 1);
+        if (pos < RERANK_MAX && !s_fail) glog[LOG_CAP / 2 - 1 - pos] = rec;
       }
     }
     __syncthreads();
     R = s_R;
+    R2 = s_R2;
   }
   if (threadIdx.x == 0) {
     int fail = s_fail;
-    if (R > RERANK_MAX) { fail = 1; R = RERANK_MAX; }
+    if (R + R2 > RERANK_MAX) { fail = 1; R = min(R, RERANK_MAX); }   // the two regions would overlap
     atomicAdd(p.sc->stat_sum + 0, (unsigned long long)total);
     atomicAdd(p.sc->stat_sum + 1, (unsigned long long)R);
     atomicMax(p.sc->stat_max + 0, total);
@@ -865,6 +882,7 @@ select_kernel(const FinParams p) {
       p.fail_list[slot] = (int)q;
     }
     p.rr[q] = fail ? -1 : R;
+    p.rr2[q] = fail ? 0 : R2;
   }
 }
 
@@ -927,16 +945,136 @@ rerank_kernel(const FinParams p) {
   }
 }
 
-// output: order the re-ranked rows by (fp64 distance, index), emit k, monitor the error bound
+// fp64 distance of one base row to the query by one warp; the operation order (float4 per lane,
+// stride 128, one fma chain per lane, xor-shuffle tree) is the one every exact path uses
+__device__ __forceinline__ double warp_row_distance(const float* __restrict__ qv, const float* __restrict__ bv,
+                                                    int d, int metric, double qn2, int lane) {
+  double acc = 0.0, bn2 = 0.0;
+  for (int c2 = lane * 4; c2 < d; c2 += 128) {
+    const float4 q4 = *reinterpret_cast<const float4*>(qv + c2);
+    const float4 b4 = *reinterpret_cast<const float4*>(bv + c2);
+    const double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
+    if (metric == NWK_METRIC_COSINE) {
+      bn2 = fma(b0, b0, bn2); bn2 = fma(b1, b1, bn2);
+      bn2 = fma(b2, b2, bn2); bn2 = fma(b3, b3, bn2);
+    }
+    if (metric == NWK_METRIC_SQEUCLIDEAN) {
+      const double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
+      acc = fma(e0, e0, acc); acc = fma(e1, e1, acc);
+      acc = fma(e2, e2, acc); acc = fma(e3, e3, acc);
+    } else {
+      acc = fma((double)q4.x, b0, acc); acc = fma((double)q4.y, b1, acc);
+      acc = fma((double)q4.z, b2, acc); acc = fma((double)q4.w, b3, acc);
+    }
+  }
+  double dist = warp_sum(acc);
+  if (metric == NWK_METRIC_COSINE) bn2 = warp_sum(bn2);
+  if (metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(metric, dist, qn2, bn2);
+  return dist;
+}
+
+// rerank, bulk-copy variant (rows of up to ~12 KB): every warp pulls RPW candidate rows into
+// shared memory with cp.async.bulk (no registers tied up while the gather is in flight; two
+// CTAs per SM keep ~200 KB of row reads outstanding) and then accumulates them in fp64 with
+// the same operation order as rerank_kernel.  HBM gather bound: 4*d bytes per kept row.
+template <int RPW>
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_bulk_kernel(const FinParams p) {
+  extern __shared__ __align__(128) unsigned char rrb_smem[];
+  constexpr int WARPS = RR_THREADS / 32;
+  constexpr int BR = WARPS * RPW;                          // rows per CTA batch
+  const int d = p.d;
+  float* s_q = reinterpret_cast<float*>(rrb_smem);         // [d]
+  float* s_rows = s_q + d;                                 // [WARPS][RPW][d]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + (size_t)BR * d);   // [WARPS]
+  const long long q = blockIdx.x;
+  const int R = p.rr[q];
+  if (R <= 0 || (int)blockIdx.y * BR >= R) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) ptx::mbar_init(&bars[warp], 1);
+  ptx::fence_barrier_init();
+  __syncthreads();
+  const double qn2 = p.qn2[q];
+  const unsigned long long* glog = p.log + q * LOG_CAP;
+  double* gdist = reinterpret_cast<double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
+  float* my_rows = s_rows + (size_t)warp * RPW * d;
+  uint32_t phase = 0;
+  bool q_loaded = false;
+
+  for (int i0 = blockIdx.y * BR; i0 < R; i0 += gridDim.y * BR) {        // CTA-uniform
+    const int wbase = i0 + warp * RPW;
+    const int nrows = max(0, min(RPW, R - wbase));                      // warp-uniform
+    if (nrows > 0) {
+      long long myrow = 0;
+      if (lane < nrows) myrow = (long long)(glog[wbase + lane] & 0xffffffffull);
+      if (phase) ptx::fence_proxy_async();       // the buffers were last read through the generic proxy
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_expect_tx(&bars[warp], (uint32_t)nrows * (uint32_t)d * 4u);
+      __syncwarp();
+      if (lane < nrows) ptx::bulk_load_1d(my_rows + (size_t)lane * d, p.base + myrow * d, (uint32_t)d * 4u, &bars[warp]);
+    }
+    if (!q_loaded) {                                                     // overlaps with the row copies
+      for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(s_q + i) = __ldg(reinterpret_cast<const float4*>(p.query + q * d + i));
+      __syncthreads();
+      q_loaded = true;
+    }
+    if (nrows > 0) {
+      if (!ptx::mbar_wait(&bars[warp], phase & 1u, &p.sc->err, 105)) return;
+      double acc[RPW], bn2[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) { acc[r] = 0.0; bn2[r] = 0.0; }
+      for (int c2 = lane * 4; c2 < d; c2 += 128) {
+        const float4 q4 = *reinterpret_cast<const float4*>(s_q + c2);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          if (r < nrows) {
+            const float4 b4 = *reinterpret_cast<const float4*>(my_rows + (size_t)r * d + c2);
+            const double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
+            if (p.metric == NWK_METRIC_COSINE) {
+              bn2[r] = fma(b0, b0, bn2[r]); bn2[r] = fma(b1, b1, bn2[r]);
+              bn2[r] = fma(b2, b2, bn2[r]); bn2[r] = fma(b3, b3, bn2[r]);
+            }
+            if (p.metric == NWK_METRIC_SQEUCLIDEAN) {
+              const double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
+              acc[r] = fma(e0, e0, acc[r]); acc[r] = fma(e1, e1, acc[r]);
+              acc[r] = fma(e2, e2, acc[r]); acc[r] = fma(e3, e3, acc[r]);
+            } else {
+              acc[r] = fma((double)q4.x, b0, acc[r]); acc[r] = fma((double)q4.y, b1, acc[r]);
+              acc[r] = fma((double)q4.z, b2, acc[r]); acc[r] = fma((double)q4.w, b3, acc[r]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        if (r < nrows) {
+          double dist = warp_sum(acc[r]);
+          if (p.metric == NWK_METRIC_COSINE) bn2[r] = warp_sum(bn2[r]);
+          if (p.metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(p.metric, dist, qn2, bn2[r]);
+          if (lane == 0) gdist[wbase + r] = dist;
+        }
+      }
+      ++phase;
+    }
+  }
+}
+
+// output: order the re-ranked rows by (fp64 distance, index), pull in the few rows of the outer
+// band that can still matter, emit k, monitor the error bound
 __global__ void __launch_bounds__(OUT_THREADS)
 output_kernel(const FinParams p) {
   __shared__ double s_key[RERANK_MAX];
   __shared__ long long s_id[RERANK_MAX];
+  __shared__ float s_akey[64];                 // approximate keys of the outer-band rows taken in
   __shared__ float s_ratio[OUT_THREADS / 32];
+  __shared__ int s_nx;
   const long long q = blockIdx.x;
   const int R = p.rr[q];
   if (R <= 0) return;
-  const int r2 = max(next_pow2(R), 2);
+  const int R2 = p.rr2[q];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int r2 = max(next_pow2(R), 2);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const unsigned long long* glog = p.log + q * LOG_CAP;
   const double* gdist = reinterpret_cast<const double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
@@ -947,6 +1085,7 @@ output_kernel(const FinParams p) {
   const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
   const double key_scale = (p.metric == NWK_METRIC_COSINE) ? sqrt(qn2) : 1.0;
   float ratio = 0.f;
+  if (threadIdx.x == 0) s_nx = 0;
   for (int i = threadIdx.x; i < r2; i += blockDim.x) {
     double dist = INF;
     long long id = 0x7fffffffffffffffLL;
@@ -964,10 +1103,57 @@ output_kernel(const FinParams p) {
     s_key[i] = dist;
     s_id[i] = id;
   }
+  block_bitonic_sort(s_key, s_id, r2);
+
+  if (R2 > 0) {
+    // D_k = exact k-th distance among the inner band >= the true k-th distance, so a row outside
+    // the inner band belongs to the answer only if its approximate key is <= key(D_k) + eps
+    const double bound = (s_key[p.k - 1] - key_shift) * key_scale + eps;
+    __syncthreads();                           // every thread has read s_key[k-1] before the tail is reused
+    for (int i = threadIdx.x; i < R2; i += blockDim.x) {
+      const unsigned long long rec = glog[LOG_CAP / 2 - 1 - i];
+      const float akey = ord2f((uint32_t)(rec >> 32));
+      if ((double)akey <= bound) {
+        const int pos = atomicAdd(&s_nx, 1);
+        if (pos < 64 && R + pos < RERANK_MAX) {
+          s_id[R + pos] = (long long)(rec & 0xffffffffull);
+          s_akey[pos] = akey;
+        }
+      }
+    }
+    __syncthreads();
+    const int nx = s_nx;
+    if (nx > 0) {
+      if (nx > 64 || R + nx > RERANK_MAX) {
+        // cannot happen unless the inner band's k-th distance sits a whole eps above a_k for
+        // dozens of rows: hand the query to the exact scan
+        if (threadIdx.x == 0) {
+          const int slot = atomicAdd(&p.sc->fail_cnt, 1);
+          p.fail_list[slot] = (int)q;
+        }
+        return;
+      }
+      for (int e = warp; e < nx; e += OUT_THREADS / 32) {
+        const long long row = s_id[R + e];
+        double dist = warp_row_distance(p.query + q * p.d, p.base + row * p.d, p.d, p.metric, qn2, lane);
+        if (lane == 0) {
+          if (dist == dist) ratio = fmaxf(ratio, (float)(fabs((double)s_akey[e] - (dist - key_shift) * key_scale) / eps));
+          else dist = INF;
+          s_key[R + e] = dist;
+        }
+      }
+      const int r3 = max(next_pow2(R + nx), 2);
+      __syncthreads();
+      for (int i = R + nx + threadIdx.x; i < r3; i += blockDim.x) { s_key[i] = INF; s_id[i] = 0x7fffffffffffffffLL; }
+      r2 = r3;
+      block_bitonic_sort(s_key, s_id, r2);
+      if (threadIdx.x == 0) atomicAdd(p.sc->stat_sum + 1, (unsigned long long)nx);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
-  if ((threadIdx.x & 31) == 0) s_ratio[threadIdx.x >> 5] = ratio;
-  block_bitonic_sort(s_key, s_id, r2);
+  if (lane == 0) s_ratio[warp] = ratio;
+  __syncthreads();
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
     p.out_dist[q * p.k + j] = (float)s_key[j];
     p.out_idx[q * p.k + j] = s_id[j] + p.id_offset;
@@ -1082,7 +1268,7 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
   bytes += align_up((size_t)nq * 4, 256);                   // cnt
   bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
-  bytes += align_up((size_t)nq * 4, 256) * 3;               // fail list, rows-to-rerank, eps
+  bytes += align_up((size_t)nq * 4, 256) * 4;               // fail list, rows-to-rerank (two bands), eps
   bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
   bytes += align_up((size_t)nq * 2 * SAMPLE_M * 4, 256);    // half-sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
@@ -1105,6 +1291,26 @@ static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMa
   return NWK_OK;
 }
 
+// rows each warp of rerank_bulk_kernel stages at once: the CTA's (1 + 8*rpw) rows of d floats
+// must leave room for two CTAs per SM; 0 = rows too long, use the register-path rerank_kernel
+constexpr int RR_BULK_SMEM_MAX = 112 * 1024;
+static int rerank_bulk_smem(int d, int rpw) { return (1 + (RR_THREADS / 32) * rpw) * d * 4 + 128; }
+static int rerank_rows_per_warp(int d) {
+  for (int rpw = 4; rpw >= 1; rpw >>= 1)
+    if (rerank_bulk_smem(d, rpw) <= RR_BULK_SMEM_MAX) return rpw;
+  return 0;
+}
+static int rerank_bulk_optin() {
+  static bool done = false;
+  if (!done) {
+    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
+    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
+    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
+    done = true;
+  }
+  return NWK_OK;
+}
+
 int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
            unsigned int flags, nwk_knn_stats* stats, cudaStream_t s) {
@@ -1120,6 +1326,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   unsigned long long* log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
   int* fail_list = ar.take<int>((size_t)nq);
   int* rr = ar.take<int>((size_t)nq);
+  int* rr2 = ar.take<int>((size_t)nq);
   float* epsq = ar.take<float>((size_t)nq);
   double* qn2 = ar.take<double>((size_t)nq);
   float* slist = ar.take<float>((size_t)nq * 2 * SAMPLE_M);
@@ -1208,7 +1415,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   FinParams f{};
   f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
   f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
-  f.rr = rr; f.epsq = epsq; f.qn2 = qn2;
+  f.rr = rr; f.rr2 = rr2; f.epsq = epsq; f.qn2 = qn2;
   // Relative error of acc against sum |q_i b_i| <= |q||b|:
   //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
   //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
@@ -1224,15 +1431,24 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     }
     select_kernel<<<(unsigned)nq, SEL_THREADS, LOG_CAP * 8, s>>>(f);
     NWK_LAUNCH_CHECK();
-    const int rr_smem = (d + 3) / 4 * 16;
-    static int rr_optin = 48 * 1024;
-    if (rr_smem > rr_optin) {
-      NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
-      rr_optin = rr_smem;
-    }
-    // grid.y blocks of 32 rows each stride over the query's R rows (R is only known on the device)
+    // grid.y blocks stride over the query's R rows (R is only known on the device)
     dim3 rgrid((unsigned)nq, 8);
-    rerank_kernel<<<rgrid, RR_THREADS, rr_smem, s>>>(f);
+    const int rpw = rerank_rows_per_warp(d);
+    if (rpw > 0) {
+      NWK_TRY(rerank_bulk_optin());
+      const int smem = rerank_bulk_smem(d, rpw);
+      if (rpw == 4) rerank_bulk_kernel<4><<<rgrid, RR_THREADS, smem, s>>>(f);
+      else if (rpw == 2) rerank_bulk_kernel<2><<<rgrid, RR_THREADS, smem, s>>>(f);
+      else rerank_bulk_kernel<1><<<rgrid, RR_THREADS, smem, s>>>(f);
+    } else {
+      const int rr_smem = (d + 3) / 4 * 16;
+      static int rr_optin = 48 * 1024;
+      if (rr_smem > rr_optin) {
+        NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
+        rr_optin = rr_smem;
+      }
+      rerank_kernel<<<rgrid, RR_THREADS, rr_smem, s>>>(f);
+    }
     NWK_LAUNCH_CHECK();
     output_kernel<<<(unsigned)nq, OUT_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();
