@@ -37,6 +37,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 
 #include "nwk_common.cuh"
@@ -101,6 +102,7 @@ struct TcParams {
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
+  int sWarm;                // SAMPLE: 1 = start every part with the short warm-up list (large samples only)
   int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (<= SAMPLE_MAX_PARTS)
   const float* alpha;       // [nT*TB]   (SAMPLE mode: the sample rows' values, [nS*TB])
   const float* beta;        // [nT*TB]
@@ -312,26 +314,29 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
   if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
 }
 
-// tau_q = SAMPLE_M-th smallest of the two half-sample lists of query q (one warp per query)
+// tau_q = SAMPLE_M-th smallest key of the union of the query's per-part lists (one warp per
+// query): bitwise search for the largest ordered key t with fewer than SAMPLE_M list entries
+// below it.  Lists that were never written hold +inf.
 __global__ void __launch_bounds__(256)
-tau_merge_kernel(const float* __restrict__ slist, long long nq, float* __restrict__ tau) {
+tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, float* __restrict__ tau) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * 8 + warp;
   if (q >= nq) return;
-  // both lists are ascending: merge-path by rank.  Element a[i] of list A has rank
-  // i + #(b < a[i]) (+ ties broken towards A); the element with rank SAMPLE_M-1 is the answer.
-  const float a = slist[(q * 2 + 0) * SAMPLE_M + lane];
-  const float b = slist[(q * 2 + 1) * SAMPLE_M + lane];
-  int ra = lane, rb = lane;
+  uint32_t v[SAMPLE_MAX_PARTS];
 #pragma unroll
-  for (int j = 0; j < SAMPLE_M; ++j) {
-    const float bj = __shfl_sync(0xffffffffu, b, j);
-    const float aj = __shfl_sync(0xffffffffu, a, j);
-    ra += (bj < a) ? 1 : 0;
-    rb += (aj <= b) ? 1 : 0;
+  for (int i = 0; i < SAMPLE_MAX_PARTS; ++i)
+    v[i] = i < parts ? f2ord(slist[(q * parts + i) * SAMPLE_M + lane]) : 0xffffffffu;
+  uint32_t ans = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = ans | (1u << bit);
+    int below = 0;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PARTS; ++i) below += (v[i] < trial) ? 1 : 0;
+    below = __reduce_add_sync(0xffffffffu, below);
+    if (below < SAMPLE_M) ans = trial;
   }
-  if (ra == SAMPLE_M - 1) tau[q] = a;
-  if (rb == SAMPLE_M - 1) tau[q] = b;
+  if (lane == 0) tau[q] = ord2f(ans);
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -447,7 +452,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG);
+      ptx::mbar_init(&tempty_bar[a], MODE == MODE_SAMPLE ? 4 : (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG);
       ptx::mbar_init(&abfull_bar[a], 1);
     }
     ptx::fence_barrier_init();
@@ -519,7 +524,115 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 4 + 4 * EPI_WG) {
+  } else if (MODE == MODE_SAMPLE && warp >= 4 && warp < 8) {
+    // ===== sample epilogue: one warpgroup; thread <-> TMEM lane <-> query row of the tile.
+    // Each thread keeps the SAMPLE_M smallest keys of its part of the sample in registers.
+    // Keys below the running threshold are only *queued* (one predicated shared-memory store
+    // per element, no branches in the unrolled loop); the queue is merged into the list when
+    // some lane's queue fills up, so a hit in one lane does not stall the other 31.  A part
+    // starts with a cheap warm-up: the SAMPLE_WARM smallest keys of its first 128 rows give the
+    // first threshold (about 3 % of the rows pass it), instead of 1000 full-length insertions.
+    // Any threshold yields an exact result; the sample only steers the candidate count. =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    float* s_queue = reinterpret_cast<float*>(s_app) + row_in_tile;       // slot i at s_queue[i * TQ]
+    Sched<MODE> sch(p);
+    int qt, t; bool first, last;
+    int acc = 0; uint32_t acc_phase = 0;
+    const float INF = __int_as_float(0x7f800000);
+    float tau = INF;
+    long long q = 0;
+    float lst[SAMPLE_M];
+    int cnt = 0, warm = 0;
+    bool ok = true;
+    while (ok && sch.next(qt, t, first, last)) {
+      if (first) {
+        q = (long long)qt * TQ + row_in_tile;
+        cnt = 0;
+        // without the warm-up every key is admitted until the list is full
+        warm = p.sWarm ? 0 : SAMPLE_WARM;
+        tau = (p.sWarm || q < p.nq) ? INF : -INF;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_M; ++j) lst[j] = INF;
+      }
+      if (!ptx::mbar_wait(&abfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
+      if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
+      const float4* al4 = reinterpret_cast<const float4*>(s_ab + acc * 2 * TB);
+      const float4* be4 = al4 + TB / 4;
+
+      // merge the queued keys into the list (every lane walks its own queue; +inf is a no-op)
+      auto flush = [&]() {
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        for (int i = 0; i < maxc; ++i) {
+          const float key = (i < cnt) ? s_queue[i * TQ] : INF;
+#pragma unroll
+          for (int m = SAMPLE_M - 1; m > 0; --m) lst[m] = fmaxf(lst[m - 1], fminf(lst[m], key));
+          lst[0] = fminf(lst[0], key);
+        }
+        cnt = 0;
+        tau = fminf(tau, lst[SAMPLE_M - 1]);
+      };
+      auto chunk = [&](const uint32_t (&cur)[32], int ch) {
+        if (warm < SAMPLE_WARM) {                           // warp-uniform
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 al = al4[ch * 8 + j4];
+            const float4 be = be4[ch * 8 + j4];
+            const float k4[4] = {fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x), fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y),
+                                 fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z), fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+              for (int m = SAMPLE_WARM - 1; m > 0; --m) lst[m] = fmaxf(lst[m - 1], fminf(lst[m], k4[e]));
+              lst[0] = fminf(lst[0], k4[e]);
+            }
+          }
+          if (++warm == SAMPLE_WARM) tau = (q < p.nq) ? lst[SAMPLE_WARM - 1] : -INF;
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 al = al4[ch * 8 + j4];
+            const float4 be = be4[ch * 8 + j4];
+            const float k4[4] = {fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x), fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y),
+                                 fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z), fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k4[e] < tau) { s_queue[cnt * TQ] = k4[e]; ++cnt; }
+          }
+          if (__any_sync(0xffffffffu, cnt > SAMPLE_QCAP - 32)) flush();
+        }
+      };
+
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+      for (int cp = 0; cp < TB / 32; cp += 2) {
+        ptx::tmem_wait_ld();
+        ptx::tmem_ld_32x32(taddr + (cp + 1) * 32, vb);
+        chunk(va, cp);
+        ptx::tmem_wait_ld();
+        if (cp + 2 < TB / 32) ptx::tmem_ld_32x32(taddr + (cp + 2) * 32, va);
+        chunk(vb, cp + 1);
+      }
+      ptx::tmem_wait_ld();
+      __syncwarp();
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // one arrival per epilogue warp
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      if (last) {
+        flush();
+        if (q < p.nq) {
+          // this CTA covered one part of the query tile's sample: publish its list, tau_merge_kernel
+          // takes the SAMPLE_M-th smallest of the union
+          float* dst = p.slist + (q * sch.sParts + (sch.u % sch.sParts)) * SAMPLE_M;
+#pragma unroll
+          for (int j = 0; j < SAMPLE_M; ++j) dst[j] = lst[j];
+        }
+      }
+    }
+  } else if (MODE != MODE_SAMPLE && warp >= 4 && warp < 4 + 4 * EPI_WG) {
     // ===== epilogue: EPI_WG warpgroups of 128 threads; thread <-> TMEM lane <-> query row of the
     // tile; warpgroup g owns the column chunks [g*CPW, (g+1)*CPW) of every accumulator tile =====
     constexpr int CPW = (TB / 32) / EPI_WG;          // 32-column chunks per warpgroup
@@ -533,19 +646,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     const float INF = __int_as_float(0x7f800000);
     float tau = -INF;
     long long q = 0;
-    float lst[SAMPLE_M];      // SAMPLE: ascending list of the smallest keys seen (registers)
     int nst = 0;              // FILTER: records staged in this thread's shared-memory slots
     bool ok = true;
     while (ok && sch.next(qt, t, first, last)) {
       if (first) {
         q = (long long)qt * TQ + row_in_tile;
-        if (MODE == MODE_FILTER) {
-          tau = (q < p.nq) ? p.tau[q] : -INF;
-        } else if (MODE == MODE_SAMPLE) {
-          tau = (q < p.nq) ? INF : -INF;
-#pragma unroll
-          for (int j = 0; j < SAMPLE_M; ++j) lst[j] = INF;
-        }
+        if (MODE == MODE_FILTER) tau = (q < p.nq) ? p.tau[q] : -INF;
       }
       if (MODE != MODE_DUMP) {
         if (!ptx::mbar_wait(&abfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
@@ -559,7 +665,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       const float4* al4 = reinterpret_cast<const float4*>(s_al);
       const float4* be4 = reinterpret_cast<const float4*>(s_be);
       const long long row0 = (long long)t * TB;
-      const int nch = (MODE == MODE_SAMPLE) ? p.sChunks : CPW;
 
       // ---- fast path: one FFMA + compare per element, hits only recorded as bit masks ----
       // (the unrolled body stays small enough for the instruction cache; everything rare is
@@ -570,12 +675,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         hit[ci] = 0;
-        if (MODE == MODE_SAMPLE && ci >= nch) continue;   // warp-uniform
         const int ch = c0 + ci;
         ptx::tmem_wait_ld();
         uint32_t(&cur)[32] = (ci & 1) ? vb : va;
         uint32_t(&nxt)[32] = (ci & 1) ? va : vb;
-        if (ci + 1 < CPW && ci + 1 < nch) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
+        if (ci + 1 < CPW) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
         if (MODE == MODE_DUMP) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -642,35 +746,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           }
         }
         }
-      } else if (MODE == MODE_SAMPLE) {
-        uint32_t anyhit = 0;
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) anyhit |= hit[ci];
-        if (__any_sync(0xffffffffu, anyhit != 0)) {
-#pragma unroll
-          for (int ci = 0; ci < CPW; ++ci) s_mask[ci * (TQ * EPI_WG) + etid] = hit[ci];   // thread-private slots
-#pragma unroll 1
-          for (int ci = 0; ci < nch; ++ci) {
-            const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
-            uint32_t um = __reduce_or_sync(0xffffffffu, mine);
-            while (um) {
-              const int j = __ffs(um) - 1;
-              um &= um - 1;
-              const int col = (c0 + ci) * 32 + j;
-              const uint32_t v = ptx::tmem_ld_32x1(taddr + col);
-              ptx::tmem_wait_ld();
-              const float key = fmaf(s_be[col], __uint_as_float(v), s_al[col]);   // bit-identical to the fast path
-              if (((mine >> j) & 1u) && key < tau) {
-                // insert into the ascending register list and drop the largest:
-                // new[i] = max(old[i-1], min(old[i], key)) -- every slot independent
-#pragma unroll
-                for (int i = SAMPLE_M - 1; i > 0; --i) lst[i] = fmaxf(lst[i - 1], fminf(lst[i], key));
-                lst[0] = fminf(lst[0], key);
-                tau = lst[SAMPLE_M - 1];
-              }
-            }
-          }
-        }
       }
       __syncwarp();
       ptx::tc_fence_before();
@@ -680,13 +755,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       ptx::mbar_arrive(&tempty_bar[acc]);
 #endif
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      if (MODE == MODE_SAMPLE && last && q < p.nq) {
-        // this CTA covered one half of the query tile's sample: publish its list, tau_merge_kernel
-        // takes the SAMPLE_M-th smallest of the union
-        float* dst = p.slist + (q * 2 + (sch.u % sch.sParts)) * SAMPLE_M;
-#pragma unroll
-        for (int j = 0; j < SAMPLE_M; ++j) dst[j] = lst[j];
-      }
       if (MODE == MODE_FILTER && last && nst > 0) {
         const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)nst);
         for (int j = 0; j < nst; ++j)
@@ -886,36 +954,64 @@ select_kernel(const FinParams p) {
   }
 }
 
-// rerank: fp64 distance of every kept row, RR_ROWS rows in flight per warp (HBM gather bound)
+// rerank: fp64 distance of every row of the inner band.  HBM gather bound (4*d bytes per row):
+// a warp accumulates RR_ROWS rows at a time (they share the query loads and conversions) and,
+// before it starts on a batch, asks L2 to fetch the rows of its next batch (prefetch.global.L2,
+// no registers or shared memory tied up), so most row reads are L2 hits and the DRAM gather
+// runs a batch ahead of the arithmetic.  (Measured alternatives: staging the rows with
+// cp.async.bulk, with or without a multi-stage ring, was 10-150 % slower than plain loads.)
 __global__ void __launch_bounds__(RR_THREADS, 4)
 rerank_kernel(const FinParams p) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   float* s_q = reinterpret_cast<float*>(rr_smem);                                           // [d]
   const long long q = blockIdx.x;
   const int R = p.rr[q];
-  if (R <= 0 || (int)blockIdx.y * RR_BLOCK_ROWS >= R) return;
+  const int Y = gridDim.y, y = blockIdx.y;
+  if (R <= 0 || y * RR_BLOCK_ROWS >= R) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x * 4; i < p.d; i += blockDim.x * 4)
-    *reinterpret_cast<float4*>(s_q + i) = __ldg(reinterpret_cast<const float4*>(p.query + q * p.d + i));
-  __syncthreads();
-  const double qn2 = p.qn2[q];
   const unsigned long long* glog = p.log + q * LOG_CAP;
   double* gdist = reinterpret_cast<double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
+  const int d = p.d;
+  // batch jj of this warp covers the log entries [first(jj), first(jj) + RR_ROWS)
+  auto first = [&](int jj) { return ((jj * Y + y) * (RR_THREADS / 32) + warp) * RR_ROWS; };
+  auto load_id = [&](int jj) -> int {                        // row ids fit 31 bits (tc_path_supported)
+    const int i = first(jj) + lane;
+    return (lane < RR_ROWS && i < R) ? (int)(glog[i] & 0xffffffffull) : -1;
+  };
+  auto prefetch = [&](int ids) {
+#pragma unroll
+    for (int r = 0; r < RR_ROWS; ++r) {
+      const int row = __shfl_sync(0xffffffffu, ids, r);
+      if (row >= 0)
+        for (int off = lane * 32; off < d; off += 32 * 32)     // one 128-byte line per lane
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.base + (long long)row * d + off));
+    }
+  };
+  int id_cur = load_id(0);
+  int id_nxt = load_id(1);
+  prefetch(id_cur);
+  for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(s_q + i) = __ldg(reinterpret_cast<const float4*>(p.query + q * d + i));
+  __syncthreads();
+  const double qn2 = p.qn2[q];
 
-  for (int i0 = blockIdx.y * RR_BLOCK_ROWS + warp * RR_ROWS; i0 < R; i0 += gridDim.y * RR_BLOCK_ROWS) {
-    long long rows[RR_ROWS];
+  for (int jj = 0; first(jj) < R; ++jj) {                    // warp-uniform
+    prefetch(id_nxt);
+    const int id_nn = load_id(jj + 2);
+    const int i0 = first(jj);
+    int rows[RR_ROWS];
     double acc[RR_ROWS], bn2[RR_ROWS];
 #pragma unroll
     for (int r = 0; r < RR_ROWS; ++r) {
       acc[r] = 0.0; bn2[r] = 0.0;
-      rows[r] = (i0 + r < R) ? (long long)(glog[i0 + r] & 0xffffffffull) : -1;
+      rows[r] = __shfl_sync(0xffffffffu, id_cur, r);
     }
-    for (int c2 = lane * 4; c2 < p.d; c2 += 128) {
+    for (int c2 = lane * 4; c2 < d; c2 += 128) {
       const float4 q4 = *reinterpret_cast<const float4*>(s_q + c2);
       float4 b4[RR_ROWS];
 #pragma unroll
       for (int r = 0; r < RR_ROWS; ++r)
-        b4[r] = rows[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.base + rows[r] * p.d + c2))
+        b4[r] = rows[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.base + (long long)rows[r] * d + c2))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < RR_ROWS; ++r) {
@@ -942,6 +1038,8 @@ rerank_kernel(const FinParams p) {
       if (p.metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(p.metric, dist, qn2, bn2[r]);
       if (lane == 0 && rows[r] >= 0) gdist[i0 + r] = dist;
     }
+    id_cur = id_nxt;
+    id_nxt = id_nn;
   }
 }
 
@@ -971,93 +1069,6 @@ __device__ __forceinline__ double warp_row_distance(const float* __restrict__ qv
   if (metric == NWK_METRIC_COSINE) bn2 = warp_sum(bn2);
   if (metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(metric, dist, qn2, bn2);
   return dist;
-}
-
-// rerank, bulk-copy variant (rows of up to ~12 KB): every warp pulls RPW candidate rows into
-// shared memory with cp.async.bulk (no registers tied up while the gather is in flight; two
-// CTAs per SM keep ~200 KB of row reads outstanding) and then accumulates them in fp64 with
-// the same operation order as rerank_kernel.  HBM gather bound: 4*d bytes per kept row.
-template <int RPW>
-__global__ void __launch_bounds__(RR_THREADS)
-rerank_bulk_kernel(const FinParams p) {
-  extern __shared__ __align__(128) unsigned char rrb_smem[];
-  constexpr int WARPS = RR_THREADS / 32;
-  constexpr int BR = WARPS * RPW;                          // rows per CTA batch
-  const int d = p.d;
-  float* s_q = reinterpret_cast<float*>(rrb_smem);         // [d]
-  float* s_rows = s_q + d;                                 // [WARPS][RPW][d]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + (size_t)BR * d);   // [WARPS]
-  const long long q = blockIdx.x;
-  const int R = p.rr[q];
-  if (R <= 0 || (int)blockIdx.y * BR >= R) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) ptx::mbar_init(&bars[warp], 1);
-  ptx::fence_barrier_init();
-  __syncthreads();
-  const double qn2 = p.qn2[q];
-  const unsigned long long* glog = p.log + q * LOG_CAP;
-  double* gdist = reinterpret_cast<double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
-  float* my_rows = s_rows + (size_t)warp * RPW * d;
-  uint32_t phase = 0;
-  bool q_loaded = false;
-
-  for (int i0 = blockIdx.y * BR; i0 < R; i0 += gridDim.y * BR) {        // CTA-uniform
-    const int wbase = i0 + warp * RPW;
-    const int nrows = max(0, min(RPW, R - wbase));                      // warp-uniform
-    if (nrows > 0) {
-      long long myrow = 0;
-      if (lane < nrows) myrow = (long long)(glog[wbase + lane] & 0xffffffffull);
-      if (phase) ptx::fence_proxy_async();       // the buffers were last read through the generic proxy
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_expect_tx(&bars[warp], (uint32_t)nrows * (uint32_t)d * 4u);
-      __syncwarp();
-      if (lane < nrows) ptx::bulk_load_1d(my_rows + (size_t)lane * d, p.base + myrow * d, (uint32_t)d * 4u, &bars[warp]);
-    }
-    if (!q_loaded) {                                                     // overlaps with the row copies
-      for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4)
-        *reinterpret_cast<float4*>(s_q + i) = __ldg(reinterpret_cast<const float4*>(p.query + q * d + i));
-      __syncthreads();
-      q_loaded = true;
-    }
-    if (nrows > 0) {
-      if (!ptx::mbar_wait(&bars[warp], phase & 1u, &p.sc->err, 105)) return;
-      double acc[RPW], bn2[RPW];
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) { acc[r] = 0.0; bn2[r] = 0.0; }
-      for (int c2 = lane * 4; c2 < d; c2 += 128) {
-        const float4 q4 = *reinterpret_cast<const float4*>(s_q + c2);
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-          if (r < nrows) {
-            const float4 b4 = *reinterpret_cast<const float4*>(my_rows + (size_t)r * d + c2);
-            const double b0 = b4.x, b1 = b4.y, b2 = b4.z, b3 = b4.w;
-            if (p.metric == NWK_METRIC_COSINE) {
-              bn2[r] = fma(b0, b0, bn2[r]); bn2[r] = fma(b1, b1, bn2[r]);
-              bn2[r] = fma(b2, b2, bn2[r]); bn2[r] = fma(b3, b3, bn2[r]);
-            }
-            if (p.metric == NWK_METRIC_SQEUCLIDEAN) {
-              const double e0 = (double)q4.x - b0, e1 = (double)q4.y - b1, e2 = (double)q4.z - b2, e3 = (double)q4.w - b3;
-              acc[r] = fma(e0, e0, acc[r]); acc[r] = fma(e1, e1, acc[r]);
-              acc[r] = fma(e2, e2, acc[r]); acc[r] = fma(e3, e3, acc[r]);
-            } else {
-              acc[r] = fma((double)q4.x, b0, acc[r]); acc[r] = fma((double)q4.y, b1, acc[r]);
-              acc[r] = fma((double)q4.z, b2, acc[r]); acc[r] = fma((double)q4.w, b3, acc[r]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        if (r < nrows) {
-          double dist = warp_sum(acc[r]);
-          if (p.metric == NWK_METRIC_COSINE) bn2[r] = warp_sum(bn2[r]);
-          if (p.metric != NWK_METRIC_SQEUCLIDEAN) dist = finish_metric(p.metric, dist, qn2, bn2[r]);
-          if (lane == 0) gdist[wbase + r] = dist;
-        }
-      }
-      ++phase;
-    }
-  }
 }
 
 // output: order the re-ranked rows by (fp64 distance, index), pull in the few rows of the outer
@@ -1256,7 +1267,16 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
     pl.ns_pad = (pl.ns + TB - 1) / TB * TB;
     pl.nS = (int)(pl.ns_pad / TB);
     pl.sChunks = TB / 32;
-    pl.sParts = (2 * pl.nQT <= sms && pl.nS >= 2) ? 2 : 1;
+    // split each query tile's scan of the sample into parts so that all SMs work: pick the
+    // part count with the fewest tile-times on the critical path (every part pays ~3 tile-times
+    // of list warm-up and publication)
+    pl.sParts = 1;
+    long long best = -1;
+    for (int parts = 1; parts <= SAMPLE_MAX_PARTS && parts <= pl.nS; ++parts) {
+      const long long waves = ((long long)pl.nQT * parts + sms - 1) / sms;
+      const long long cost = waves * ((pl.nS + parts - 1) / parts + 3);
+      if (best < 0 || cost < best) { best = cost; pl.sParts = parts; }
+    }
   }
   return pl;
 }
@@ -1270,7 +1290,7 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
   bytes += align_up((size_t)nq * 4, 256) * 4;               // fail list, rows-to-rerank (two bands), eps
   bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
-  bytes += align_up((size_t)nq * 2 * SAMPLE_M * 4, 256);    // half-sample lists
+  bytes += align_up((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M * 4, 256);    // per-part sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
   bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
   bytes += align_up((size_t)pl.ns_pad * 4, 256) * 2;        // sample alpha, beta
@@ -1288,26 +1308,6 @@ static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMa
   else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
   else tc_kernel<MODE_DUMP, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
   NWK_LAUNCH_CHECK();
-  return NWK_OK;
-}
-
-// rows each warp of rerank_bulk_kernel stages at once: the CTA's (1 + 8*rpw) rows of d floats
-// must leave room for two CTAs per SM; 0 = rows too long, use the register-path rerank_kernel
-constexpr int RR_BULK_SMEM_MAX = 112 * 1024;
-static int rerank_bulk_smem(int d, int rpw) { return (1 + (RR_THREADS / 32) * rpw) * d * 4 + 128; }
-static int rerank_rows_per_warp(int d) {
-  for (int rpw = 4; rpw >= 1; rpw >>= 1)
-    if (rerank_bulk_smem(d, rpw) <= RR_BULK_SMEM_MAX) return rpw;
-  return 0;
-}
-static int rerank_bulk_optin() {
-  static bool done = false;
-  if (!done) {
-    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
-    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
-    NWK_CUDA(cudaFuncSetAttribute(rerank_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_BULK_SMEM_MAX));
-    done = true;
-  }
   return NWK_OK;
 }
 
@@ -1329,7 +1329,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   int* rr2 = ar.take<int>((size_t)nq);
   float* epsq = ar.take<float>((size_t)nq);
   double* qn2 = ar.take<double>((size_t)nq);
-  float* slist = ar.take<float>((size_t)nq * 2 * SAMPLE_M);
+  float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M);
   __half* bh = ar.take<__half>((size_t)nb * pl.dh);
   __half* qh = ar.take<__half>((size_t)nq * pl.dh);
   float* salpha = ar.take<float>((size_t)pl.ns_pad);
@@ -1389,7 +1389,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
 
   if (pl.sample) {
-    fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * 2 * SAMPLE_M, HUGE_VALF);
+    fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_M, HUGE_VALF);
     NWK_LAUNCH_CHECK();
     // the sample pass scans the compact matrix of sampled rows with their own alpha / beta
     CUtensorMap tm_s;
@@ -1397,9 +1397,14 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     else NWK_TRY(make_tmap(&tm_s, srows, pl.ns, d, false, TB));
     TcParams ps = p;
     ps.alpha = salpha; ps.beta = sbeta; ps.nT = pl.nS;
+    // The warm-up threshold (4th smallest key of a part's first 128 sample rows) must stay above
+    // the final tau (the SAMPLE_M-th smallest of all ns rows), or list entries go missing and tau
+    // comes out too large: the chance per list is P(Poisson(128 * SAMPLE_M / ns) >= 4), 0.2 % at
+    // ns = 8192 and 1e-5 at the 31 250 rows of a 1M-row base; smaller samples insert every key.
+    ps.sWarm = pl.ns >= 8192 ? 1 : 0;
     int grid = pl.sParts * pl.nQT < sms ? pl.sParts * pl.nQT : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s));
-    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, tau);
+    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, pl.sParts, tau);
     NWK_LAUNCH_CHECK();
   } else {
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
@@ -1431,24 +1436,18 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     }
     select_kernel<<<(unsigned)nq, SEL_THREADS, LOG_CAP * 8, s>>>(f);
     NWK_LAUNCH_CHECK();
-    // grid.y blocks stride over the query's R rows (R is only known on the device)
-    dim3 rgrid((unsigned)nq, 8);
-    const int rpw = rerank_rows_per_warp(d);
-    if (rpw > 0) {
-      NWK_TRY(rerank_bulk_optin());
-      const int smem = rerank_bulk_smem(d, rpw);
-      if (rpw == 4) rerank_bulk_kernel<4><<<rgrid, RR_THREADS, smem, s>>>(f);
-      else if (rpw == 2) rerank_bulk_kernel<2><<<rgrid, RR_THREADS, smem, s>>>(f);
-      else rerank_bulk_kernel<1><<<rgrid, RR_THREADS, smem, s>>>(f);
-    } else {
-      const int rr_smem = (d + 3) / 4 * 16;
-      static int rr_optin = 48 * 1024;
-      if (rr_smem > rr_optin) {
-        NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
-        rr_optin = rr_smem;
-      }
-      rerank_kernel<<<rgrid, RR_THREADS, rr_smem, s>>>(f);
+    const int rr_smem = (d + 3) / 4 * 16;
+    static int rr_optin = 48 * 1024;
+    if (rr_smem > rr_optin) {
+      NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
+      rr_optin = rr_smem;
     }
+    // a query's batches are dealt over grid.y CTAs; every warp prefetches one batch ahead
+    // (measured best split: 1 at d = 128, 4 at d = 768, 8 at d = 1536 -- longer rows want more
+    // CTAs per query in flight)
+    long long ysplit = std::max<long long>(((long long)sms * 8 + nq - 1) / nq, (d + 96) / 192);
+    dim3 rgrid((unsigned)nq, (unsigned)(ysplit < 1 ? 1 : (ysplit > 8 ? 8 : ysplit)));
+    rerank_kernel<<<rgrid, RR_THREADS, rr_smem, s>>>(f);
     NWK_LAUNCH_CHECK();
     output_kernel<<<(unsigned)nq, OUT_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();
