@@ -7,6 +7,6 @@ $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
 $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|select_kernel|rerank_kernel|output_kernel|baseprep" -s 18 -c 6 -o gpurun_out/prof_hot_$W $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|select_kernel|rerank_kernel|output_kernel|baseprep|tau_merge|qprep" -s 24 -c 8 -f -o gpurun_out/prof_hot_$W $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 tail -2 gpurun_out/ncu_full.log | cut -c1-200

@@ -112,6 +112,35 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     print(metric, (nq, nb, d, k), st, res)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"], ids=["single-cta", "cta-pair"])
+@pytest.mark.parametrize("nq,nb,d,k,metric", [
+    (333, 5003, 100, 100, "sqeuclidean"),    # odd number of query tiles: the last pair has an empty half
+    (100, 3000, 64, 50, "cosine"),           # one query tile: the second CTA of the pair has no queries at all
+    (1000, 10000, 384, 100, "dot"),
+    (700, 300000, 64, 100, "cosine"),        # sample large enough for the warm-up list and several parts per query tile
+])
+def test_tc_filter_variants(cuda_device, monkeypatch, pair, nq, nb, d, k, metric):
+    """The CTA-pair (cta_group::2) and single-CTA filter kernels must both reproduce the oracle,
+    whatever the planner would have picked for the shape (NWK_PAIR is the library's experiment switch)."""
+    from neighborhoodwatch_b200 import knn
+    monkeypatch.setenv("NWK_PAIR", pair)
+    base = synth.vectors(nb, d, 4321)
+    q = synth.vectors(nq, d, 8765)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric, id_offset=11)
+    st = dict(knn.last_stats)
+    assert st["path"] == 1, st
+    assert st["n_fallback_queries"] <= max(1, nq // 100), st
+    assert st["max_candidates"] <= 4096, st
+    if nb > 100000:     # too large for the numpy oracle on every query: check a sample of them
+        sel = np.arange(0, nq, 7)
+        t_d, t_i = ko.knn_f64(base, q[sel], k, metric, return_f64=True)
+        res = ko.compare_knn(got_d.cpu().numpy()[sel], got_i.cpu().numpy()[sel], base, q[sel], metric, t_d, t_i + 11,
+                             rtol=1e-5, atol=1e-6, tie_rtol=1e-6, id_offset=11)
+    else:
+        res = _check(got_d, got_i, base, q, k, metric, id_offset=11)
+    print(pair, (nq, nb, d, k, metric), st, res)
+
+
 @pytest.mark.parametrize("metric", ko.METRICS)
 def test_tc_knn_parity_tf32_operands(cuda_device, metric):
     from neighborhoodwatch_b200 import knn
