@@ -245,6 +245,14 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
   return v;
 }
 
+// eight consecutive columns of the warp's 32 lanes
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // K-major operand tile staged by TMA with 128-byte swizzle: rows of 128 B, 8-row groups
 // 1024 B apart.  (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).)

@@ -76,19 +76,12 @@ static_assert(((LOG_TARGET / SAMPLE_M) & (LOG_TARGET / SAMPLE_M - 1)) == 0, "sam
 constexpr int RERANK_MAX = 2048;               // most rows re-ranked in fp64 per query (fp64 results live in log slots [LOG_CAP/2, LOG_CAP))
 static_assert(RERANK_MAX <= LOG_CAP / 2, "re-ranked distances alias the upper half of the query's log");
 constexpr int TC_MAX_K = 256;
-#ifndef NWK_SLOW_BATCH
-#define NWK_SLOW_BATCH 1          // hit columns whose TMEM loads are in flight together (1 = one at a time)
-#endif
 #ifndef NWK_WARP_ARRIVE
 #define NWK_WARP_ARRIVE 1         // 1: one tempty arrival per epilogue warp, 0: one per thread
 #endif
 #ifndef NWK_APPEND_NOINLINE
 #define NWK_APPEND_NOINLINE 0     // measured: an out-of-line call costs +11 % at d=128 (register save/restore)
 #endif
-#ifndef NWK_SLOW_DYNAMIC
-#define NWK_SLOW_DYNAMIC 0        // 1: filter slow path as one rolled loop over chunks (masks via smem)
-#endif
-
 enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
 enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
 
@@ -98,6 +91,7 @@ template <bool F16> struct Op {
   static constexpr int UMMA_K = F16 ? 16 : 8;
 };
 
+struct Scalars;
 struct TcParams {
   int nKB;
   long long nq, nb;
@@ -111,6 +105,8 @@ struct TcParams {
   float* slist;             // SAMPLE: [nq][sParts][SAMPLE_M] smallest keys per query and sample part
   unsigned int* cnt;        // [nq]
   unsigned long long* log;  // [nq][LOG_CAP]
+  const Scalars* sc;        // direct keys: the scales that make up kscale
+  int metric;
   float* dump;              // MODE_DUMP: [TQ][TB]
   int dump_qt, dump_t;
   int* err;
@@ -123,7 +119,7 @@ struct Scalars {            // one block of device scalars, zeroed per call
   int fail_cnt;
   unsigned int stat_max[2];
   unsigned int err_ratio;   // max |approx key - exact key| / eps over re-ranked rows (float bits)
-  unsigned int pad;
+  unsigned int babsmax;     // max finite |b_ij| (float bits): the global base scale of the direct-key filter
   unsigned long long stat_sum[2];
 };
 
@@ -132,12 +128,18 @@ struct Scalars {            // one block of device scalars, zeroed per call
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 qmax_kernel(const float* __restrict__ q, long long n, unsigned int* __restrict__ out) {
+  // largest finite magnitude (fmaxf drops NaN, infinities are skipped); n % 4 == 0 (d % 4 == 0)
+  const float INF = __int_as_float(0x7f800000);
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(q[i]));
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n >> 2); i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(q4 + i);
+    const float a0 = fabsf(v.x), a1 = fabsf(v.y), a2 = fabsf(v.z), a3 = fabsf(v.w);
+    m = fmaxf(m, fmaxf(fmaxf(a0 < INF ? a0 : 0.f, a1 < INF ? a1 : 0.f), fmaxf(a2 < INF ? a2 : 0.f, a3 < INF ? a3 : 0.f)));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f && m < __int_as_float(0x7f800000)) atomicMax(out, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // power-of-two exponent s such that maxabs * 2^s lies in [2^14, 2^15): every element of the
@@ -172,6 +174,20 @@ __device__ __forceinline__ float pow2f(int e) {
   return __int_as_float((e + 127) << 23);
 }
 
+// Direct keys (fp16 operands, dot / cosine): every base row is scaled by the same power of two
+// 2^sbg (after normalisation to unit length for cosine), so the accumulator orders the rows by
+// itself: key = kscale * acc with kscale = -2^-(sq + sbg).  The filter epilogue then needs no
+// per-column alpha / beta at all (their shared-memory reads bound the general epilogue).
+__device__ __forceinline__ int direct_base_exp(int direct, int metric, const Scalars* sc) {
+  if (!direct) return 0;
+  if (metric == NWK_METRIC_COSINE) return 14;          // unit rows: |element| <= 1 -> <= 2^14
+  return f16_scale_exp(__uint_as_float(sc->babsmax));
+}
+__device__ __forceinline__ float direct_kscale(int metric, const Scalars* sc) {
+  const int sq = f16_scale_exp(__uint_as_float(sc->qabsmax));
+  return -pow2f(-(sq + direct_base_exp(1, metric, sc)));
+}
+
 // one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale.
 // The row is read once: up to ROW_CACHE float4 per lane stay in registers between the
 // norm / max pass and the conversion pass (d <= 1024); longer rows re-read their tail (L1/L2).
@@ -201,7 +217,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
-                __half* __restrict__ bh, const SampleOut so) {
+                __half* __restrict__ bh, const SampleOut so, const int direct) {
   constexpr int ROW_CACHE = 8;
   if (so.stride_log2 >= 0) {
     const float PINF = __int_as_float(0x7f800000);
@@ -214,6 +230,8 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float INF = __int_as_float(0x7f800000);
   const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
+  // direct keys (F16 only): every row shares one scale, so key = kscale * acc for the whole call
+  const int sbg = direct_base_exp(direct, metric, sc);
   float local_max = 0.f;
   for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
     if (row >= nb) {
@@ -248,6 +266,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     }
     a = warp_sum(a);
     int sb = 0;
+    bool row_ok = true;
     // is this row its block's sample row?
     long long srow = -1;
     if (so.stride_log2 >= 0) {
@@ -269,7 +288,17 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (!(mx < INF)) mx = 0.f;             // inf / nan rows: leave unscaled (they never rank)
       sb = f16_scale_exp(mx);
-      const float scale = pow2f(sb);         // exact power of two: v * scale is exact up to fp16 rounding
+      float scale = pow2f(sb);               // exact power of two: v * scale is exact up to fp16 rounding
+      if (direct) {
+        // rows that cannot rank (a nan entry, a zero vector under cosine) become zero rows flagged
+        // by alpha = +inf; the filter's slow path adds alpha to the key of every hit.  (Rows with
+        // infinite entries keep them: their accumulators come out +-inf / nan like their distances.)
+        row_ok = (a == a) && (metric != NWK_METRIC_COSINE || a > 0.0);
+        sb = sbg;
+        scale = pow2f(sbg);
+        if (metric == NWK_METRIC_COSINE) scale = (float)(1.0 / sqrt(a)) * scale;   // unit row at 2^sbg
+        if (!row_ok) scale = 0.f;
+      }
       __half* hrow = bh + row * dh;
       __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * dh : nullptr;
 #pragma unroll
@@ -282,6 +311,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
           uint2 pk;
           pk.x = *reinterpret_cast<unsigned int*>(&h01);
           pk.y = *reinterpret_cast<unsigned int*>(&h23);
+          if (!row_ok) pk = make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(hrow + c) = pk;
           if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
         }
@@ -294,6 +324,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         uint2 pk;
         pk.x = *reinterpret_cast<unsigned int*>(&h01);
         pk.y = *reinterpret_cast<unsigned int*>(&h23);
+        if (!row_ok) pk = make_uint2(0u, 0u);
         *reinterpret_cast<uint2*>(hrow + c) = pk;
         if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
       }
@@ -302,7 +333,10 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       // acc = 2^(sq+sb) * (q.b) up to operand rounding: fold the scale into beta (exact)
       const float unscale = pow2f(-(sq + sb));
       float al = 0.f, be = -unscale;
-      if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f * unscale; }
+      if (direct) {
+        // be is the same for every row (direct_kscale); al only flags rows that must never rank
+        if (!row_ok) { al = INF; be = 0.f; }
+      } else if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f * unscale; }
       else if (metric == NWK_METRIC_COSINE) {
         if (a > 0.0) be = (float)(-1.0 / sqrt(a)) * unscale; else { al = INF; be = 0.f; }
       }
@@ -428,11 +462,12 @@ struct Sched {
 // the leader CTA (cluster rank 0) issues one M=256 MMA for both; each CTA's TMEM receives its
 // 128 queries x 256 rows and runs the same epilogue as the single-CTA kernel.  TcParams.nQT then
 // counts query-tile PAIRS.
-template <int MODE, bool F16, bool CTA2 = false>
+template <int MODE, bool F16, bool CTA2 = false, bool DIRECT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
   static_assert(!CTA2 || (MODE == MODE_FILTER && F16), "CTA pairs are built for the fp16 filter pass");
+  static_assert(!DIRECT || (MODE == MODE_FILTER && F16), "direct keys are built for the fp16 filter pass");
   constexpr int BK = Op<F16>::BK;
   constexpr int UMMA_K = Op<F16>::UMMA_K;
   constexpr int NST = CTA2 ? PAIR_STAGES : STAGES;
@@ -525,7 +560,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       while (ok && sch.next(qt, t, first, last)) {
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
         ptx::tc_fence_after();
-        if (MODE != MODE_DUMP && !CTA2) {
+        if (MODE != MODE_DUMP && !CTA2 && !DIRECT) {
           // the epilogue has released this stage: refill its alpha / beta tile (2 x 1 KB)
           float* ab = s_ab + acc * 2 * TB;
           ptx::mbar_arrive_expect_tx(&abfull_bar[acc], 2 * TB * 4);
@@ -556,7 +591,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (CTA2 && warp == 3) {
+  } else if (CTA2 && !DIRECT && warp == 3) {
     // ===== alpha / beta loader of a CTA pair: each CTA refills its own copy of the tile's
     // 256 alpha / beta values once its epilogue warps have released the accumulator stage =====
     if (lane == 0) {
@@ -693,6 +728,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     int acc = 0; uint32_t acc_phase = 0;
     const float INF = __int_as_float(0x7f800000);
     float tau = -INF;
+    float thr = INF;          // DIRECT: acc > thr  <=>  kscale * acc < tau  (kscale = -2^m: exact)
+    const float kscale = DIRECT ? direct_kscale(p.metric, p.sc) : 0.f;
     long long q = 0;
     int nst = 0;              // FILTER: records staged in this thread's shared-memory slots
     bool ok = true;
@@ -700,8 +737,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (first) {
         q = (long long)(CTA2 ? qt * 2 + (int)rank : qt) * TQ + row_in_tile;
         if (MODE == MODE_FILTER) tau = (q < p.nq) ? p.tau[q] : -INF;
+        if (DIRECT) thr = tau / kscale;
       }
-      if (MODE != MODE_DUMP) {
+      if (MODE != MODE_DUMP && !DIRECT) {
         if (!ptx::mbar_wait(&abfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
       }
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
@@ -714,15 +752,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       const float4* be4 = reinterpret_cast<const float4*>(s_be);
       const long long row0 = (long long)t * TB;
 
-      // ---- fast path: one FFMA + compare per element, hits only recorded as bit masks ----
-      // (the unrolled body stays small enough for the instruction cache; everything rare is
-      //  in the single slow loop below, which re-reads the hit columns from TMEM)
+      // ---- fast path: per group of 8 columns one running minimum of the keys (FMNMX3) and one
+      // compare; a lane only records WHICH groups hold a key below its threshold (bit ci*4+g of
+      // `hits`).  General keys: alpha_j + beta_j * acc (one FFMA per element, alpha / beta read as
+      // broadcast LDS.128 -- those reads are what bounds this variant).  Direct keys: the
+      // accumulator itself against thr = tau / kscale, no shared-memory traffic at all. ----
       uint32_t va[32], vb[32];
-      uint32_t hit[CPW];
+      uint32_t hits = 0;
       ptx::tmem_ld_32x32(taddr + c0 * 32, va);
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
-        hit[ci] = 0;
         const int ch = c0 + ci;
         ptx::tmem_wait_ld();
         uint32_t(&cur)[32] = (ci & 1) ? vb : va;
@@ -732,74 +771,80 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             p.dump[(long long)row_in_tile * TB + ch * 32 + j] = __uint_as_float(cur[j]);
-        } else {
-          uint32_t mask = 0;
+        } else if (DIRECT) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 al = al4[ch * 8 + j4];           // shared-memory broadcast reads
-            const float4 be = be4[ch * 8 + j4];
-            if (fmaf(be.x, __uint_as_float(cur[4 * j4 + 0]), al.x) < tau) mask |= 1u << (4 * j4 + 0);
-            if (fmaf(be.y, __uint_as_float(cur[4 * j4 + 1]), al.y) < tau) mask |= 1u << (4 * j4 + 1);
-            if (fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z) < tau) mask |= 1u << (4 * j4 + 2);
-            if (fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w) < tau) mask |= 1u << (4 * j4 + 3);
+          for (int g = 0; g < 4; ++g) {
+            float m = fmaxf(__uint_as_float(cur[8 * g]), __uint_as_float(cur[8 * g + 1]));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2)
+              m = fmaxf(m, fmaxf(__uint_as_float(cur[8 * g + j]), __uint_as_float(cur[8 * g + j + 1])));
+            if (m > thr) hits |= 1u << (ci * 4 + g);
           }
-          hit[ci] = mask;
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float m = INF;
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const float4 al = al4[ch * 8 + g * 2 + j4];           // shared-memory broadcast reads
+              const float4 be = be4[ch * 8 + g * 2 + j4];
+              const int e = 8 * g + 4 * j4;
+              m = fminf(m, fminf(fmaf(be.x, __uint_as_float(cur[e + 0]), al.x), fmaf(be.y, __uint_as_float(cur[e + 1]), al.y)));
+              m = fminf(m, fminf(fmaf(be.z, __uint_as_float(cur[e + 2]), al.z), fmaf(be.w, __uint_as_float(cur[e + 3]), al.w)));
+            }
+            if (m < tau) hits |= 1u << (ci * 4 + g);
+          }
         }
       }
       ptx::tmem_wait_ld();
 
-      // ---- slow path (rare): columns where some lane of the warp has a hit ----
+      // ---- slow path (rare): groups where some lane of the warp has a hit.  One rolled loop:
+      // re-read the group's 8 columns from TMEM, recompute the keys (bit-identical to the fast
+      // path) and append the records of the lanes that hit. ----
       if (MODE == MODE_FILTER) {
-        // unrolled over this warpgroup's chunks so the hit masks stay in registers; the
-        // append itself is one out-of-line function (keeps the loop body in the I-cache)
-#if NWK_SLOW_DYNAMIC
-        uint32_t anyhit = 0;
+        uint32_t um = __reduce_or_sync(0xffffffffu, hits);
+        while (um) {                                   // warp-uniform
+          const int b = __ffs(um) - 1;
+          um &= um - 1;
+          const int colb = c0 * 32 + b * 8;            // first column of the group inside the tile
+          uint32_t v[8];
+          ptx::tmem_ld_32x8(taddr + colb, v);
+          ptx::tmem_wait_ld();
+          if ((hits >> b) & 1u) {
+            float key[8];
+            uint32_t m8 = 0;
 #pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) anyhit |= hit[ci];
-        if (__any_sync(0xffffffffu, anyhit != 0)) {
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) s_mask[ci * (TQ * EPI_WG) + etid] = hit[ci];
-#pragma unroll 1
-        for (int ci = 0; ci < CPW; ++ci) {
-          const uint32_t mine = s_mask[ci * (TQ * EPI_WG) + etid];
-#else
-        {
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) {
-          const uint32_t mine = hit[ci];
-#endif
-          uint32_t um = __reduce_or_sync(0xffffffffu, mine);
-          while (um) {
-            // up to 4 hit columns per round: their TMEM loads are issued back to back and
-            // waited for once (the load latency, not the arithmetic, is the cost here)
-            int jj[NWK_SLOW_BATCH];
-            uint32_t vv[NWK_SLOW_BATCH];
-#pragma unroll
-            for (int b = 0; b < NWK_SLOW_BATCH; ++b) {
-              jj[b] = um ? __ffs(um) - 1 : -1;
-              um &= um - 1;                          // (0 & anything stays 0)
-              if (jj[b] >= 0) vv[b] = ptx::tmem_ld_32x1(taddr + (c0 + ci) * 32 + jj[b]);   // warp-uniform
+            for (int j = 0; j < 8; ++j) {
+              if (DIRECT) {
+                key[j] = kscale * __uint_as_float(v[j]);
+                if (__uint_as_float(v[j]) > thr) m8 |= 1u << j;
+              } else {
+                key[j] = fmaf(s_be[colb + j], __uint_as_float(v[j]), s_al[colb + j]);
+                if (key[j] < tau) m8 |= 1u << j;
+              }
             }
-            ptx::tmem_wait_ld();
+            while (m8) {                               // per lane: usually a single column
+              const int j = __ffs(m8) - 1;
+              m8 &= m8 - 1;
+              float kj = key[0];
 #pragma unroll
-            for (int b = 0; b < NWK_SLOW_BATCH; ++b) {
-              if (jj[b] < 0) continue;               // warp-uniform
-              const int col = (c0 + ci) * 32 + jj[b];
-              const float key = fmaf(s_be[col], __uint_as_float(vv[b]), s_al[col]);   // bit-identical to the fast path
-              if (((mine >> jj[b]) & 1u) && key < tau)
-                nst = append_record((static_cast<unsigned long long>(f2ord(key)) << 32) |
-                                        static_cast<unsigned long long>(row0 + col),
+              for (int jj = 1; jj < 8; ++jj) kj = (j == jj) ? key[jj] : kj;
+              const long long row = row0 + colb + j;
+              // direct keys carry no alpha: the zero rows of the tile padding are dropped here, the
+              // (data-dependent, rare) rows flagged by alpha = +inf when select_kernel reads the log
+              if (!DIRECT || row < p.nb)
+                nst = append_record((static_cast<unsigned long long>(f2ord(kj)) << 32) |
+                                        static_cast<unsigned long long>(row),
                                     nst, s_app + etid, TQ * EPI_WG, p.cnt + q, p.log + q * LOG_CAP);
             }
           }
-        }
         }
       }
       __syncwarp();
       ptx::tc_fence_before();
       if (CTA2) {
         // the accumulator stage belongs to the pair's MMA issuer (leader CTA); alpha / beta are local
-        if (lane == 0) { ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); ptx::mbar_arrive(&abempty_bar[acc]); }
+        if (lane == 0) { ptx::mbar_arrive_cluster(&tempty_bar[acc], 0); if (!DIRECT) ptx::mbar_arrive(&abempty_bar[acc]); }
       } else {
 #if NWK_WARP_ARRIVE
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // one arrival per epilogue warp
@@ -842,6 +887,8 @@ struct FinParams {
   Scalars* sc;
   float c_rel;                 // relative error constant of the operand format
   int f16;                     // fp16 operands: adds the subnormal-quantisation term
+  int direct;                  // direct keys: one global base scale (base-side quantisation term, cosine pre-normalisation)
+  const float* alpha;          // direct keys: +inf marks base rows that must never rank
   float* out_dist; long long* out_idx;
   int* fail_list;
 };
@@ -871,7 +918,12 @@ select_kernel(const FinParams p) {
   const int c = (int)min(total, (unsigned int)LOG_CAP);
   unsigned long long* glog = p.log + q * LOG_CAP;
 
-  for (int i = threadIdx.x; i < c; i += blockDim.x) s_log[i] = glog[i];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    unsigned long long rec = glog[i];
+    // direct keys: rows flagged as unrankable (alpha = +inf) were logged with the key of a zero row
+    if (p.direct && !(p.alpha[rec & 0xffffffffull] < __int_as_float(0x7f800000))) rec |= 0xffffffff00000000ull;
+    s_log[i] = rec;
+  }
   if (warp == 0) {
     // |q|^2 in the same operation order as scan_dist_kernel
     double a = 0.0;
@@ -946,6 +998,15 @@ select_kernel(const FinParams p) {
         const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
         eps_dot += qquant * bnmax;
         eps_cos += qquant;
+        if (p.direct) {
+          // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
+          // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
+          // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
+          const int sbg = direct_base_exp(1, p.metric, p.sc);
+          const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
+          eps_dot += bquant;
+          eps_cos += bquant + ldexp(1.0, -22) * qn;
+        }
       }
       eps = eps_dot;
       if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
@@ -1276,6 +1337,8 @@ static int tc_optin() {
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -1396,6 +1459,16 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (ar.off > ws_bytes) return fail(NWK_ERR_WORKSPACE, "workspace too small for the tensor-core path");
   size_t scan_ws_bytes = ws_bytes - ar.off;
 
+  // Filter variant.  CTA pairs (cta_group::2) when the query tiles pair up without much waste and
+  // the MMAs of a tile outlast its epilogue (measured: -6 % filter time at d = 768, -10 % at
+  // d = 1536, but +25 % at d = 128, where the epilogue is the limit and the pair couples two of
+  // them).  Direct keys (no alpha / beta in the epilogue) where the epilogue is the limit: short
+  // rows; dot and cosine only (sq-L2 needs the per-row |b|^2 term).
+  bool pair = f16 && sms >= 2 && d >= 512 && (pl.nQT % 2 == 0 || pl.nQT >= 8);
+  if (const char* e = getenv("NWK_PAIR")) pair = f16 && sms >= 2 && atoi(e) != 0;   // experiment switch
+  bool direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && pl.dh <= 256;
+  if (const char* e = getenv("NWK_DIRECT")) direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && atoi(e) != 0;
+
   const long long launches0 = g_launches.load();
   const bool profile = stats && (flags & NWK_FLAG_PROFILE);
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1423,8 +1496,13 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
       so.ns = pl.ns; so.ns_pad = pl.ns_pad;
       so.rows = srows; so.alpha = salpha; so.beta = sbeta;
     }
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
-    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so);
+    if (direct && metric != NWK_METRIC_COSINE) {
+      // the one extra pass the direct keys cost: the global scale needs max |b_ij| before any row is converted
+      qmax_kernel<<<sms * 8, 256, 0, s>>>(base, nb * d, &sc->babsmax);
+      NWK_LAUNCH_CHECK();
+    }
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, 0);
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[1], s);
@@ -1442,6 +1520,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
+  p.sc = sc; p.metric = metric;
 
   if (pl.sample) {
     fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_M, HUGE_VALF);
@@ -1466,11 +1545,6 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[2], s);
-  // CTA pairs (cta_group::2) when the query tiles pair up without much waste and the MMAs of a
-  // tile outlast its epilogue (measured: -6 % filter time at d = 768, -10 % at d = 1536, but
-  // +25 % at d = 128, where the epilogue is the limit and the pair couples two of them)
-  bool pair = f16 && sms >= 2 && d >= 512 && (pl.nQT % 2 == 0 || pl.nQT >= 8);
-  if (const char* e = getenv("NWK_PAIR")) pair = f16 && sms >= 2 && atoi(e) != 0;   // experiment switch
   if (pair) {
     const int clusters = sms / 2;
     TcParams pp = p;
@@ -1491,8 +1565,13 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true>, tm_q, tm_bh, pp));
+    if (direct) NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true, true>, tm_q, tm_bh, pp));
+    else NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true>, tm_q, tm_bh, pp));
     count_launch();
+  } else if (direct) {
+    int grid = pl.nUnits < sms ? pl.nUnits : sms;
+    tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    NWK_LAUNCH_CHECK();
   } else {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_FILTER, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_FILTER, grid, tm_q, tm_b, p, s));
@@ -1502,7 +1581,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   FinParams f{};
   f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
   f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
-  f.rr = rr; f.rr2 = rr2; f.epsq = epsq; f.qn2 = qn2;
+  f.rr = rr; f.rr2 = rr2; f.epsq = epsq; f.qn2 = qn2; f.direct = direct ? 1 : 0; f.alpha = alpha;
   // Relative error of acc against sum |q_i b_i| <= |q||b|:
   //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
   //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
@@ -1614,12 +1693,12 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_LAUNCH_CHECK();
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample);
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);

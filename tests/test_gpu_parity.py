@@ -112,6 +112,7 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     print(metric, (nq, nb, d, k), st, res)
 
 
+@pytest.mark.parametrize("direct", ["0", "1"], ids=["alpha-beta-keys", "direct-keys"])
 @pytest.mark.parametrize("pair", ["0", "1"], ids=["single-cta", "cta-pair"])
 @pytest.mark.parametrize("nq,nb,d,k,metric", [
     (333, 5003, 100, 100, "sqeuclidean"),    # odd number of query tiles: the last pair has an empty half
@@ -119,11 +120,16 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     (1000, 10000, 384, 100, "dot"),
     (700, 300000, 64, 100, "cosine"),        # sample large enough for the warm-up list and several parts per query tile
 ])
-def test_tc_filter_variants(cuda_device, monkeypatch, pair, nq, nb, d, k, metric):
-    """The CTA-pair (cta_group::2) and single-CTA filter kernels must both reproduce the oracle,
-    whatever the planner would have picked for the shape (NWK_PAIR is the library's experiment switch)."""
+def test_tc_filter_variants(cuda_device, monkeypatch, pair, direct, nq, nb, d, k, metric):
+    """The CTA-pair (cta_group::2) and single-CTA filter kernels, with per-column alpha / beta keys
+    or direct keys (one global base scale; dot and cosine only), must all reproduce the oracle,
+    whatever the planner would have picked for the shape (NWK_PAIR / NWK_DIRECT are the library's
+    experiment switches)."""
     from neighborhoodwatch_b200 import knn
+    if direct == "1" and metric == "sqeuclidean":
+        pytest.skip("direct keys are not built for squared L2")
     monkeypatch.setenv("NWK_PAIR", pair)
+    monkeypatch.setenv("NWK_DIRECT", direct)
     base = synth.vectors(nb, d, 4321)
     q = synth.vectors(nq, d, 8765)
     got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric, id_offset=11)
@@ -163,6 +169,34 @@ def test_tc_gaussian_unnormalised(cuda_device):
         got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric=metric)
         assert knn.last_stats["path"] == 1
         _check(got_d, got_i, base, q, 100, metric)
+
+
+@pytest.mark.parametrize("direct", ["0", "1"], ids=["alpha-beta-keys", "direct-keys"])
+@pytest.mark.parametrize("metric", ["dot", "cosine"])
+def test_tc_signed_rows_with_unrankable_entries(cuda_device, monkeypatch, metric, direct):
+    """Signed vectors of very different lengths, a ragged last tile, zero vectors (no cosine) and rows
+    with inf / nan entries: such rows must never be returned, by either key form."""
+    from neighborhoodwatch_b200 import knn
+    monkeypatch.setenv("NWK_DIRECT", direct)
+    rng = np.random.default_rng(11)
+    nb, nq, d, k = 30011, 150, 96, 100
+    base = (rng.standard_normal((nb, d)) * rng.uniform(0.01, 30.0, (nb, 1))).astype(np.float32)
+    q = (rng.standard_normal((nq, d)) * 0.2).astype(np.float32)
+    bad = [3, 777, 12345, nb - 1]
+    base[bad[0]] = 0.0
+    base[bad[1], 5] = np.inf if metric == "cosine" else np.nan      # (an inf entry gives a dot product of +-inf, which ranks)
+    base[bad[2], 7] = np.nan
+    base[bad[3]] = 0.0
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric)
+    st = dict(knn.last_stats)
+    assert st["path"] == 1 and st["max_err_ratio"] <= 1.0, st
+    got_i = got_i.cpu().numpy()
+    skip = bad[1:3] if metric == "dot" else bad          # a zero vector has a dot product, but no cosine
+    assert not np.isin(got_i, skip).any()
+    keep = np.setdiff1d(np.arange(nb), skip)
+    t_d, t_i = ko.knn_f64(base[keep], q, k, metric, return_f64=True)
+    res = ko.compare_knn(got_d.cpu().numpy(), got_i, base, q, metric, t_d, keep[t_i], rtol=1e-5, atol=1e-6, tie_rtol=1e-6)
+    print(metric, direct, st, res)
 
 
 def test_tc_duplicates_fall_back_and_stay_exact(cuda_device):
