@@ -39,6 +39,7 @@
 #include <math.h>
 #include <algorithm>
 #include <stdlib.h>
+#include <vector>
 
 #include "nwk_common.cuh"
 #include "nwk_ptx.cuh"
@@ -79,9 +80,6 @@ constexpr int TC_MAX_K = 256;
 #ifndef NWK_WARP_ARRIVE
 #define NWK_WARP_ARRIVE 1         // 1: one tempty arrival per epilogue warp, 0: one per thread
 #endif
-#ifndef NWK_APPEND_NOINLINE
-#define NWK_APPEND_NOINLINE 0     // measured: an out-of-line call costs +11 % at d=128 (register save/restore)
-#endif
 enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DUMP = 2 };
 enum { ERR_PRODUCER = 101, ERR_MMA_EMPTY = 102, ERR_MMA_FULL = 103, ERR_EPI = 104 };
 
@@ -107,6 +105,9 @@ struct TcParams {
   unsigned long long* log;  // [nq][LOG_CAP]
   const Scalars* sc;        // direct keys: the scales that make up kscale
   int metric;
+  unsigned long long* prof; // NWK_DEBUG_PROF: per CTA, cycles the MMA issuer spent waiting for (accumulator, operands) and in total, tiles
+  int dbg_na;               // NWK_DEBUG_NA = 1: a single resident query buffer even where two fit
+  int dbg;                  // NWK_DEBUG_EPI (timing experiments, results are wrong): 1 = no key passes, 2 = epilogue skips the accumulators
   float* dump;              // MODE_DUMP: [TQ][TB]
   int dump_qt, dump_t;
   int* err;
@@ -380,27 +381,6 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
     p[i] = v;
 }
 
-// Stage one candidate record in the calling thread's private shared-memory slots (slot i at
-// slots[i * stride]); when all APPEND_SLOTS are used, one global atomic reserves log space for
-// the batch and the records are written out.  Returns the new number of staged records.
-#if NWK_APPEND_NOINLINE
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-int append_record(unsigned long long rec, int nst, unsigned long long* slots, int stride,
-                                          unsigned int* cnt, unsigned long long* qlog) {
-  slots[nst * stride] = rec;
-  if (++nst == APPEND_SLOTS) {
-    const unsigned int base = atomicAdd(cnt, (unsigned int)APPEND_SLOTS);
-#pragma unroll
-    for (int i = 0; i < APPEND_SLOTS; ++i)
-      if (base + i < LOG_CAP) qlog[base + i] = slots[i * stride];
-    nst = 0;
-  }
-  return nst;
-}
-
 // ---------------------------------------------------------------------------------------
 // schedule shared by the three roles of tc_kernel: the sequence of (query tile, base tile)
 // pairs this CTA walks, in an order that keeps concurrently running CTAs on the same base
@@ -462,12 +442,18 @@ struct Sched {
 // the leader CTA (cluster rank 0) issues one M=256 MMA for both; each CTA's TMEM receives its
 // 128 queries x 256 rows and runs the same epilogue as the single-CTA kernel.  TcParams.nQT then
 // counts query-tile PAIRS.
-template <int MODE, bool F16, bool CTA2 = false, bool DIRECT = false>
+// ARES = the query tile stays resident in shared memory for a whole unit (up to 16 base tiles)
+// instead of being re-fetched with every base tile: a third less L2 -> SM traffic per FLOP.  The
+// single-CTA kernel is bound by exactly that traffic (measured with the epilogue switched off:
+// 96 KB per 128 x 256 x 128 tile arrive in 1640 clk, the MMAs need 1024).  Short rows only: the
+// tile's whole K extent (p.nKB x 16 KB, at most 96 KB) must fit beside a ring of base stages.
+template <int MODE, bool F16, bool CTA2 = false, bool DIRECT = false, bool ARES = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
   static_assert(!CTA2 || (MODE == MODE_FILTER && F16), "CTA pairs are built for the fp16 filter pass");
   static_assert(!DIRECT || (MODE == MODE_FILTER && F16), "direct keys are built for the fp16 filter pass");
+  static_assert(!ARES || (MODE == MODE_FILTER && F16 && !CTA2), "resident query tiles are built for the single-CTA fp16 filter pass");
   constexpr int BK = Op<F16>::BK;
   constexpr int UMMA_K = Op<F16>::UMMA_K;
   constexpr int NST = CTA2 ? PAIR_STAGES : STAGES;
@@ -487,14 +473,23 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   unsigned long long* s_app = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES + AB_BYTES);
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES);
-  uint64_t* full_bar = bars;                       // [NST]   (CTA2: only the leader's are used)
-  uint64_t* empty_bar = bars + NST;                // [NST]
-  uint64_t* tfull_bar = bars + 2 * NST;            // [ACC_STAGES]
-  uint64_t* tempty_bar = bars + 2 * NST + ACC_STAGES;          // (CTA2: the leader's, both CTAs' epilogues arrive)
-  uint64_t* abfull_bar = bars + 2 * NST + 2 * ACC_STAGES;      // [ACC_STAGES]
-  uint64_t* abempty_bar = bars + 2 * NST + 3 * ACC_STAGES;     // [ACC_STAGES] (CTA2 only)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4 * ACC_STAGES);
-  static_assert((2 * PAIR_STAGES + 4 * ACC_STAGES) * 8 + 4 <= 256, "barrier block");
+  constexpr int NB = PAIR_STAGES;                  // barrier slots per ring (the longest ring any variant uses)
+  uint64_t* full_bar = bars;                       // [NB]   (CTA2: only the leader's are used)
+  uint64_t* empty_bar = bars + NB;                 // [NB]
+  uint64_t* tfull_bar = bars + 2 * NB;             // [ACC_STAGES]
+  uint64_t* tempty_bar = bars + 2 * NB + ACC_STAGES;           // (CTA2: the leader's, both CTAs' epilogues arrive)
+  uint64_t* abfull_bar = bars + 2 * NB + 2 * ACC_STAGES;       // [ACC_STAGES]
+  uint64_t* abempty_bar = bars + 2 * NB + 3 * ACC_STAGES;      // [ACC_STAGES] (CTA2 only)
+  uint64_t* afull_bar = bars + 2 * NB + 4 * ACC_STAGES;        // [2] (ARES: resident query tile buffers)
+  uint64_t* aempty_bar = bars + 2 * NB + 4 * ACC_STAGES + 2;   // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NB + 4 * ACC_STAGES + 4);
+  static_assert((2 * NB + 4 * ACC_STAGES + 4) * 8 + 4 <= 256, "barrier block");
+  static_assert(NST <= NB, "barrier block");
+  // ARES geometry: [nA query-tile buffers of a_bytes][nsb base stages of 32 KB] inside the same 192 KB
+  const int a_bytes = ARES ? p.nKB * STAGE_A_BYTES : 0;
+  const int nA = ARES ? ((2 * a_bytes + 4 * STAGE_B_BYTES <= STAGES * STAGE_BYTES && p.dbg_na != 1) ? 2 : 1) : 0;
+  const int nsb = ARES ? min(NB, (STAGES * STAGE_BYTES - nA * a_bytes) / STAGE_B_BYTES) : NST;
+  unsigned char* const b_ring = smem + nA * a_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -504,13 +499,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     ptx::prefetch_tensormap(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NST; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NB; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
       ptx::mbar_init(&tempty_bar[a], CTA2 ? 2 * 4 * EPI_WG
                                           : (MODE == MODE_SAMPLE ? 4 : (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG));
       ptx::mbar_init(&abfull_bar[a], 1);
       ptx::mbar_init(&abempty_bar[a], 4 * EPI_WG);
+      ptx::mbar_init(&afull_bar[a], 1);
+      ptx::mbar_init(&aempty_bar[a], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -523,17 +520,47 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  // The three control roles run as whole, converged warps: every lane walks the schedule and polls
+  // the barriers, and only the instructions that start asynchronous work sit under elect.sync.
+  // (With the role under `if (lane == 0)` the compiler wraps every tcgen05 / TMA instruction into
+  // an election loop and keeps the loop state in vector registers; measured on the MMA issuer:
+  // 560 clk to issue 8 MMAs + 2 commits and 1550 clk per trip of a 1024-clk tile.)
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      SchedT sch(p);
-      int qt, t; bool first, last;
-      int stage = 0; uint32_t phase = 0;
-      bool ok = true;
-      while (ok && sch.next(qt, t, first, last)) {
+    SchedT sch(p);
+    int qt, t; bool first, last;
+    int stage = 0; uint32_t phase = 0;
+    bool ok = true;
+    int abuf = 0; uint32_t aphase = 0;
+    while (ok && sch.next(qt, t, first, last)) {
+      if (ARES) {
+        if (first) {
+          // a new unit: its query tile goes into the next resident buffer (free once the MMAs
+          // of the unit that used it last have retired)
+          if (!ptx::mbar_wait(&aempty_bar[abuf], aphase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&afull_bar[abuf], a_bytes);
+            for (int kb = 0; kb < p.nKB; ++kb)
+              ptx::tma_load_2d(smem + abuf * a_bytes + kb * STAGE_A_BYTES, &tmap_q, &afull_bar[abuf], kb * BK, qt * TQ);
+          }
+          __syncwarp();
+          if (++abuf == nA) { abuf = 0; aphase ^= 1; }
+        }
         for (int kb = 0; kb < p.nKB; ++kb) {
           if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
-          unsigned char* sa = smem + stage * ST_BYTES;
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_B_BYTES);
+            ptx::tma_load_2d(b_ring + stage * STAGE_B_BYTES, &tmap_b, &full_bar[stage], kb * BK, t * TB);
+          }
+          __syncwarp();
+          if (++stage == nsb) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
+      for (int kb = 0; kb < p.nKB; ++kb) {
+        if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
+        unsigned char* sa = smem + stage * ST_BYTES;
+        if (ptx::elect_one()) {
           if (CTA2) {
             // both CTAs' loads are credited to the leader's barrier, which expects the bytes of both
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ST_BYTES);
@@ -544,68 +571,99 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
             ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * BK, qt * TQ);
             ptx::tma_load_2d(sa + STAGE_A_BYTES, &tmap_b, &full_bar[stage], kb * BK, t * TB);
           }
-          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread; of the leader CTA when the tile belongs to a CTA pair) =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (one warp; of the leader CTA when the tile belongs to a CTA pair) =====
+    if (rank == 0) {
       SchedT sch(p);
       int qt, t; bool first, last;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      int abuf = 0; uint32_t aphase = 0;
       const uint32_t idesc = F16 ? ptx::umma_idesc_f16(CTA2 ? 2 * TQ : TQ, TB) : ptx::umma_idesc_tf32(TQ, TB);
       bool ok = true;
+      long long w_acc = 0, w_op = 0, w_issue = 0, n_tiles = 0;
+      const long long t_begin = clock64();
       while (ok && sch.next(qt, t, first, last)) {
+        long long tw = p.prof ? clock64() : 0;
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
+        if (p.prof) { w_acc += clock64() - tw; ++n_tiles; }
         ptx::tc_fence_after();
         if (MODE != MODE_DUMP && !CTA2 && !DIRECT) {
           // the epilogue has released this stage: refill its alpha / beta tile (2 x 1 KB)
-          float* ab = s_ab + acc * 2 * TB;
-          ptx::mbar_arrive_expect_tx(&abfull_bar[acc], 2 * TB * 4);
-          ptx::bulk_load_1d(ab, p.alpha + (long long)t * TB, TB * 4, &abfull_bar[acc]);
-          ptx::bulk_load_1d(ab + TB, p.beta + (long long)t * TB, TB * 4, &abfull_bar[acc]);
+          if (ptx::elect_one()) {
+            float* ab = s_ab + acc * 2 * TB;
+            ptx::mbar_arrive_expect_tx(&abfull_bar[acc], 2 * TB * 4);
+            ptx::bulk_load_1d(ab, p.alpha + (long long)t * TB, TB * 4, &abfull_bar[acc]);
+            ptx::bulk_load_1d(ab + TB, p.beta + (long long)t * TB, TB * 4, &abfull_bar[acc]);
+          }
+          __syncwarp();
         }
         const uint32_t d_tmem = tmem_base + acc * TB;
+        if (ARES && first) {
+          if (!ptx::mbar_wait(&afull_bar[abuf], aphase, p.err, ERR_MMA_FULL)) { ok = false; break; }
+        }
         for (int kb = 0; kb < p.nKB; ++kb) {
+          tw = p.prof ? clock64() : 0;
           if (!ptx::mbar_wait(&full_bar[stage], phase, p.err, ERR_MMA_FULL)) { ok = false; break; }
+          if (p.prof) w_op += clock64() - tw;
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * ST_BYTES);
-          const uint64_t da = ptx::umma_desc_sw128(sa);
-          const uint64_t db = ptx::umma_desc_sw128(sa + STAGE_A_BYTES);
+          tw = p.prof ? clock64() : 0;
+          if (ptx::elect_one()) {
+            const uint32_t sa = ARES ? ptx::smem_u32(smem + abuf * a_bytes + kb * STAGE_A_BYTES)
+                                     : ptx::smem_u32(smem + stage * ST_BYTES);
+            const uint64_t da = ptx::umma_desc_sw128(sa);
+            const uint64_t db = ptx::umma_desc_sw128(ARES ? ptx::smem_u32(b_ring + stage * STAGE_B_BYTES) : sa + STAGE_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // one MMA consumes 32 bytes of K inside the 128 B swizzle span: +2 in 16-byte units
-            if (CTA2) ptx::mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else if (F16) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else ptx::mma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // one MMA consumes 32 bytes of K inside the 128 B swizzle span: +2 in 16-byte units
+              if (CTA2) ptx::mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else if (F16) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else ptx::mma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (CTA2) ptx::tc_commit_pair(&empty_bar[stage], 3); else ptx::tc_commit(&empty_bar[stage]);
+            // last K-block: accumulator complete -> epilogue (of both CTAs of a pair)
+            if (kb == p.nKB - 1) {
+              if (CTA2) ptx::tc_commit_pair(&tfull_bar[acc], 3); else ptx::tc_commit(&tfull_bar[acc]);
+              // the unit's MMAs are all issued: its query tile buffer is free once they retire
+              if (ARES && last) ptx::tc_commit(&aempty_bar[abuf]);
+            }
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (CTA2) ptx::tc_commit_pair(&empty_bar[stage], 3); else ptx::tc_commit(&empty_bar[stage]);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (p.prof) w_issue += clock64() - tw;
+          if (++stage == nsb) { stage = 0; phase ^= 1; }
         }
         if (!ok) break;
-        // accumulator complete -> epilogue (of both CTAs of a pair)
-        if (CTA2) ptx::tc_commit_pair(&tfull_bar[acc], 3); else ptx::tc_commit(&tfull_bar[acc]);
+        if (ARES && last) { if (++abuf == nA) { abuf = 0; aphase ^= 1; } }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.prof && lane == 0) {
+        unsigned long long* o = p.prof + (size_t)blockIdx.x * 4;
+        o[0] = (unsigned long long)w_acc; o[1] = (unsigned long long)w_op | ((unsigned long long)w_issue << 32);
+        o[2] = (unsigned long long)(clock64() - t_begin); o[3] = (unsigned long long)n_tiles;
       }
     }
   } else if (CTA2 && !DIRECT && warp == 3) {
     // ===== alpha / beta loader of a CTA pair: each CTA refills its own copy of the tile's
     // 256 alpha / beta values once its epilogue warps have released the accumulator stage =====
-    if (lane == 0) {
-      SchedT sch(p);
-      int qt, t; bool first, last;
-      int acc = 0; uint32_t acc_phase = 0;
-      while (sch.next(qt, t, first, last)) {
-        if (!ptx::mbar_wait(&abempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) break;
+    SchedT sch(p);
+    int qt, t; bool first, last;
+    int acc = 0; uint32_t acc_phase = 0;
+    while (sch.next(qt, t, first, last)) {
+      if (!ptx::mbar_wait(&abempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) break;
+      if (ptx::elect_one()) {
         float* ab = s_ab + acc * 2 * TB;
         ptx::mbar_arrive_expect_tx(&abfull_bar[acc], 2 * TB * 4);
         ptx::bulk_load_1d(ab, p.alpha + (long long)t * TB, TB * 4, &abfull_bar[acc]);
         ptx::bulk_load_1d(ab + TB, p.beta + (long long)t * TB, TB * 4, &abfull_bar[acc]);
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else if (MODE == MODE_SAMPLE && warp >= 4 && warp < 8) {
     // ===== sample epilogue: one warpgroup; thread <-> TMEM lane <-> query row of the tile.
@@ -736,7 +794,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     while (ok && sch.next(qt, t, first, last)) {
       if (first) {
         q = (long long)(CTA2 ? qt * 2 + (int)rank : qt) * TQ + row_in_tile;
-        if (MODE == MODE_FILTER) tau = (q < p.nq) ? p.tau[q] : -INF;
+        if (MODE == MODE_FILTER) tau = (q < p.nq && p.dbg != 1) ? p.tau[q] : -INF;
         if (DIRECT) thr = tau / kscale;
       }
       if (MODE != MODE_DUMP && !DIRECT) {
@@ -759,6 +817,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // accumulator itself against thr = tau / kscale, no shared-memory traffic at all. ----
       uint32_t va[32], vb[32];
       uint32_t hits = 0;
+      if (p.dbg != 2) {
       ptx::tmem_ld_32x32(taddr + c0 * 32, va);
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
@@ -797,12 +856,19 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         }
       }
       ptx::tmem_wait_ld();
+      }
 
       // ---- slow path (rare): groups where some lane of the warp has a hit.  One rolled loop:
       // re-read the group's 8 columns from TMEM, recompute the keys (bit-identical to the fast
-      // path) and append the records of the lanes that hit. ----
+      // path) and stage the records of the lanes that hit.  Every branch in it is warp-uniform
+      // (votes) and the per-lane work is predicated: divergent branches and their reconvergence
+      // cost more here than the arithmetic (measured: 30 % of the loop's stall samples).
+      // (Measured alternatives at d = 128: doing this work inside the fast path, while the values
+      // are still in registers, behind one vote per group: +18 % filter time; four groups per
+      // trip with their loads and compare chains interleaved: +9 %.) ----
       if (MODE == MODE_FILTER) {
         uint32_t um = __reduce_or_sync(0xffffffffu, hits);
+        unsigned long long* const slots = s_app + etid;
         while (um) {                                   // warp-uniform
           const int b = __ffs(um) - 1;
           um &= um - 1;
@@ -810,34 +876,45 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           uint32_t v[8];
           ptx::tmem_ld_32x8(taddr + colb, v);
           ptx::tmem_wait_ld();
-          if ((hits >> b) & 1u) {
-            float key[8];
-            uint32_t m8 = 0;
+          float key[8];
+          uint32_t m8 = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (DIRECT) {
-                key[j] = kscale * __uint_as_float(v[j]);
-                if (__uint_as_float(v[j]) > thr) m8 |= 1u << j;
-              } else {
-                key[j] = fmaf(s_be[colb + j], __uint_as_float(v[j]), s_al[colb + j]);
-                if (key[j] < tau) m8 |= 1u << j;
-              }
-            }
-            while (m8) {                               // per lane: usually a single column
-              const int j = __ffs(m8) - 1;
-              m8 &= m8 - 1;
-              float kj = key[0];
-#pragma unroll
-              for (int jj = 1; jj < 8; ++jj) kj = (j == jj) ? key[jj] : kj;
-              const long long row = row0 + colb + j;
-              // direct keys carry no alpha: the zero rows of the tile padding are dropped here, the
-              // (data-dependent, rare) rows flagged by alpha = +inf when select_kernel reads the log
-              if (!DIRECT || row < p.nb)
-                nst = append_record((static_cast<unsigned long long>(f2ord(kj)) << 32) |
-                                        static_cast<unsigned long long>(row),
-                                    nst, s_app + etid, TQ * EPI_WG, p.cnt + q, p.log + q * LOG_CAP);
+          for (int j = 0; j < 8; ++j) {
+            if (DIRECT) {
+              key[j] = __uint_as_float(v[j]);
+              if (key[j] > thr) m8 |= 1u << j;
+            } else {
+              key[j] = fmaf(s_be[colb + j], __uint_as_float(v[j]), s_al[colb + j]);
+              if (key[j] < tau) m8 |= 1u << j;
             }
           }
+          do {                                         // one trip unless a lane hit twice in the group
+            const bool has = m8 != 0;
+            const int j = has ? __ffs(m8) - 1 : 0;
+            m8 &= m8 - 1;                              // (0 stays 0)
+            float kj = key[0];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj) kj = (j == jj) ? key[jj] : kj;
+            if (DIRECT) kj *= kscale;
+            const long long row = row0 + colb + j;
+            // direct keys carry no alpha: the zero rows of the tile padding are dropped here, the
+            // (data-dependent, rare) rows flagged by alpha = +inf when select_kernel reads the log
+            const bool take = has && (!DIRECT || row < p.nb);
+            if (take)
+              slots[nst * (TQ * EPI_WG)] = (static_cast<unsigned long long>(f2ord(kj)) << 32) |
+                                           static_cast<unsigned long long>(row);
+            nst += take ? 1 : 0;
+            if (__any_sync(0xffffffffu, nst == APPEND_SLOTS)) {
+              if (nst == APPEND_SLOTS) {
+                // one global atomic reserves log space for the lane's batch of staged records
+                const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
+#pragma unroll
+                for (int i = 0; i < APPEND_SLOTS; ++i)
+                  if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = slots[i * (TQ * EPI_WG)];
+                nst = 0;
+              }
+            }
+          } while (__any_sync(0xffffffffu, m8 != 0));
         }
       }
       __syncwarp();
@@ -1339,6 +1416,8 @@ static int tc_optin() {
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -1468,6 +1547,9 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (const char* e = getenv("NWK_PAIR")) pair = f16 && sms >= 2 && atoi(e) != 0;   // experiment switch
   bool direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && pl.dh <= 256;
   if (const char* e = getenv("NWK_DIRECT")) direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && atoi(e) != 0;
+  // resident query tiles: single-CTA filter, rows of at most 6 K-blocks (d <= 384)
+  bool ares = f16 && !pair && pl.nKB <= 6;
+  if (const char* e = getenv("NWK_ARES")) ares = f16 && !pair && pl.nKB <= 6 && atoi(e) != 0;
 
   const long long launches0 = g_launches.load();
   const bool profile = stats && (flags & NWK_FLAG_PROFILE);
@@ -1521,6 +1603,14 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
   p.sc = sc; p.metric = metric;
+  if (const char* e = getenv("NWK_DEBUG_EPI")) p.dbg = atoi(e);
+  if (const char* e = getenv("NWK_DEBUG_NA")) p.dbg_na = atoi(e);
+  unsigned long long* d_prof = nullptr;
+  if (getenv("NWK_DEBUG_PROF")) {
+    NWK_CUDA(cudaMalloc(&d_prof, (size_t)sms * 4 * 8));
+    NWK_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)sms * 4 * 8, s));
+    p.prof = d_prof;
+  }
 
   if (pl.sample) {
     fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_M, HUGE_VALF);
@@ -1568,15 +1658,29 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     if (direct) NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true, true>, tm_q, tm_bh, pp));
     else NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true>, tm_q, tm_bh, pp));
     count_launch();
-  } else if (direct) {
+  } else if (direct || ares) {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
-    tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    if (direct && ares) tc_kernel<MODE_FILTER, true, false, true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    else if (direct) tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    else tc_kernel<MODE_FILTER, true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
     NWK_LAUNCH_CHECK();
   } else {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_FILTER, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_FILTER, grid, tm_q, tm_b, p, s));
   }
   if (profile) cudaEventRecord(ev[3], s);
+  if (d_prof) {
+    std::vector<unsigned long long> hp((size_t)sms * 4);
+    NWK_CUDA(cudaMemcpyAsync(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost, s));
+    NWK_CUDA(cudaStreamSynchronize(s));
+    double a = 0, o = 0, t = 0, n = 0;
+    double is = 0;
+    for (int i = 0; i < sms; ++i) { a += hp[i * 4]; o += hp[i * 4 + 1] & 0xffffffffull; is += hp[i * 4 + 1] >> 32; t += hp[i * 4 + 2]; n += hp[i * 4 + 3]; }
+    if (n > 0)
+      fprintf(stderr, "[nwk prof] MMA issuer per tile: %.0f clk total, %.0f waiting for the accumulator stage, %.0f waiting for operands, %.0f issuing MMAs + commit (%.0f tiles)\n",
+              t / n, a / n, o / n, is / n, n);
+    cudaFree(d_prof);
+  }
 
   FinParams f{};
   f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
@@ -1624,7 +1728,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (err_ratio > 1.0f)
     return fail(NWK_ERR_INTERNAL, "candidate keys exceeded the proven error bound (ratio %.3f)", err_ratio);
 
-  if (h.fail_cnt > 0 && !(flags & NWK_FLAG_NO_FALLBACK)) {
+  if (h.fail_cnt > 0 && !(flags & NWK_FLAG_NO_FALLBACK) && p.dbg == 0) {
     // uncertified queries: fp64 scan, in rounds that fit the provisioned scratch
     long long done = 0;
     while (done < h.fail_cnt) {

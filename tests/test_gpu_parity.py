@@ -113,14 +113,15 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
 
 
 @pytest.mark.parametrize("direct", ["0", "1"], ids=["alpha-beta-keys", "direct-keys"])
-@pytest.mark.parametrize("pair", ["0", "1"], ids=["single-cta", "cta-pair"])
+@pytest.mark.parametrize("pair,ares", [("0", "0"), ("0", "1"), ("1", "0")], ids=["single-cta", "single-cta-resident-queries", "cta-pair"])
 @pytest.mark.parametrize("nq,nb,d,k,metric", [
     (333, 5003, 100, 100, "sqeuclidean"),    # odd number of query tiles: the last pair has an empty half
     (100, 3000, 64, 50, "cosine"),           # one query tile: the second CTA of the pair has no queries at all
-    (1000, 10000, 384, 100, "dot"),
+    (1000, 10000, 384, 100, "dot"),           # six K-blocks: one resident query buffer, three base stages
     (700, 300000, 64, 100, "cosine"),        # sample large enough for the warm-up list and several parts per query tile
+    (600, 40000, 256, 100, "sqeuclidean"),   # four K-blocks: one resident query buffer, four base stages
 ])
-def test_tc_filter_variants(cuda_device, monkeypatch, pair, direct, nq, nb, d, k, metric):
+def test_tc_filter_variants(cuda_device, monkeypatch, pair, ares, direct, nq, nb, d, k, metric):
     """The CTA-pair (cta_group::2) and single-CTA filter kernels, with per-column alpha / beta keys
     or direct keys (one global base scale; dot and cosine only), must all reproduce the oracle,
     whatever the planner would have picked for the shape (NWK_PAIR / NWK_DIRECT are the library's
@@ -130,6 +131,7 @@ def test_tc_filter_variants(cuda_device, monkeypatch, pair, direct, nq, nb, d, k
         pytest.skip("direct keys are not built for squared L2")
     monkeypatch.setenv("NWK_PAIR", pair)
     monkeypatch.setenv("NWK_DIRECT", direct)
+    monkeypatch.setenv("NWK_ARES", ares)
     base = synth.vectors(nb, d, 4321)
     q = synth.vectors(nq, d, 8765)
     got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), k, metric=metric, id_offset=11)
