@@ -958,7 +958,7 @@ struct FinParams {
   const float* tau; const unsigned int* cnt;
   unsigned long long* log;     // [nq][LOG_CAP]; select rewrites [0,R) sorted, rerank writes fp64 at [LOG_CAP/2, LOG_CAP/2+R)
   int* rr;                     // [nq] rows to re-rank (approximate key <= a_k + eps), -1 = uncertified
-  int* rr2;                    // [nq] rows in the outer band (a_k + eps, a_k + 2 eps], parked at the end of the record half
+  int* rr2;                    // [nq] rows in the outer band (a_k + eps, a_k + 2 eps], parked at the end of the log
   float* epsq;                 // [nq] proven key error bound
   double* qn2;                 // [nq] |q|^2
   Scalars* sc;
@@ -979,164 +979,163 @@ constexpr int OUT_THREADS = 128;
 // select: find the k-th smallest logged key a_k by radix select (4 passes of 8 bits over the
 // order-preserving 32-bit keys), form the band [a_k, a_k + 2 eps], certify, and compact the R
 // records inside the band to the front of the query's log (order is irrelevant: output_kernel
-// sorts by exact distance).  Shared-memory histogram work only; ~4x cheaper than sorting the log.
+// sorts by exact distance).  One WARP per query, no block barriers: the log (8 KB on average) is
+// re-read from L1 / L2 in every pass, the histogram of a pass is 1 KB of shared memory per warp.
+// (The first version used one CTA per query with the log staged in shared memory: 0.6 ms for
+// 10 000 queries, half of it waiting at __syncthreads.)
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const FinParams p) {
-  extern __shared__ __align__(16) unsigned char sel_smem[];
-  unsigned long long* s_log = reinterpret_cast<unsigned long long*>(sel_smem);             // [LOG_CAP]
-  __shared__ unsigned int s_hist[256];
-  __shared__ double s_qn2;
-  __shared__ unsigned int s_prefix, s_kk, s_thr_ord, s_thr1_ord;
-  __shared__ int s_R, s_R2, s_fail;
-
-  const long long q = blockIdx.x;
+  __shared__ unsigned int s_hist_all[SEL_THREADS / 32][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * (SEL_THREADS / 32) + warp;
+  if (q >= p.nq) return;                         // whole warps leave; nothing below is block-wide
+  unsigned int* const hist = s_hist_all[warp];
   const unsigned int total = p.cnt[q];
   const int c = (int)min(total, (unsigned int)LOG_CAP);
-  unsigned long long* glog = p.log + q * LOG_CAP;
+  unsigned long long* const glog = p.log + q * LOG_CAP;
+  const float PINF = __int_as_float(0x7f800000);
 
-  for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    unsigned long long rec = glog[i];
-    // direct keys: rows flagged as unrankable (alpha = +inf) were logged with the key of a zero row
-    if (p.direct && !(p.alpha[rec & 0xffffffffull] < __int_as_float(0x7f800000))) rec |= 0xffffffff00000000ull;
-    s_log[i] = rec;
-  }
-  if (warp == 0) {
-    // |q|^2 in the same operation order as scan_dist_kernel
-    double a = 0.0;
+  // |q|^2 in the same operation order as scan_dist_kernel
+  double qn2 = 0.0;
+  {
     const float* qrow = p.query + q * p.d;
-    for (int c2 = lane; c2 < p.d; c2 += 32) { double v = qrow[c2]; a = fma(v, v, a); }
-    a = warp_sum(a);
-    if (lane == 0) s_qn2 = a;
+    for (int c2 = lane; c2 < p.d; c2 += 32) { const double v = qrow[c2]; qn2 = fma(v, v, qn2); }
+    qn2 = warp_sum(qn2);
   }
   const bool countable = !(total > (unsigned int)LOG_CAP || c < p.k);
-  if (threadIdx.x == 0) { s_prefix = 0; s_kk = (unsigned int)(p.k - 1); }
-  __syncthreads();
 
+  unsigned int prefix = 0;
   if (countable) {
     // radix select of the element of rank k-1 among the c keys
-    unsigned int mask = 0;
+    unsigned int kk = (unsigned int)(p.k - 1), mask = 0;
 #pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-      __syncthreads();
-      const unsigned int prefix = s_prefix;
-      for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        const unsigned int key = (unsigned int)(s_log[i] >> 32);
-        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (warp == 0) {
-        // lane l owns bins [8l, 8l+8): inclusive scan across lanes, then locate the digit
-        unsigned int loc[8], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { loc[j] = s_hist[lane * 8 + j]; sum += loc[j]; }
-        unsigned int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
+      for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+      __syncwarp();
+      for (int i = lane; i < c; i += 32) {
+        unsigned long long rec = glog[i];
+        if (shift == 24 && p.direct && !(p.alpha[rec & 0xffffffffull] < PINF)) {
+          // direct keys: rows flagged as unrankable (alpha = +inf) were logged with the key of a zero row
+          rec |= 0xffffffff00000000ull;
+          glog[i] = rec;
         }
-        const unsigned int excl = incl - sum;
-        const unsigned int kk = s_kk;
-        if (kk >= excl && kk < incl) {           // exactly one lane
-          unsigned int run = excl;
+        const unsigned int key = (unsigned int)(rec >> 32);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncwarp();
+      // lane l owns bins [8l, 8l+8): inclusive scan across lanes, then locate the digit
+      unsigned int loc[8], sum = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (kk >= run && kk < run + loc[j]) {
-              s_prefix = prefix | ((unsigned int)(lane * 8 + j) << shift);
-              s_kk = kk - run;
-            }
-            run += loc[j];
-          }
+      for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+      unsigned int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned int excl = incl - sum;
+      const bool mine = kk >= excl && kk < incl;       // exactly one lane
+      unsigned int np = prefix, nk = kk;
+      if (mine) {
+        unsigned int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kk >= run && kk < run + loc[j]) { np = prefix | ((unsigned int)(lane * 8 + j) << shift); nk = kk - run; }
+          run += loc[j];
         }
       }
+      const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+      prefix = __shfl_sync(0xffffffffu, np, src);
+      kk = __shfl_sync(0xffffffffu, nk, src);
       mask |= 255u << shift;
-      __syncthreads();
+      __syncwarp();
     }
   }
 
-  if (threadIdx.x == 0) {
-    const double qn2 = s_qn2;
-    int fail = 0;
-    double eps = 0.0;
-    unsigned int thr_ord = 0, thr1_ord = 0;
-    if (!countable) {
-      fail = 1;
-    } else {
-      // proven bound on |approximate key - exact key| for this query (DESIGN.md "error bound")
-      const double qn = sqrt(qn2);
-      const double bnmax = sqrt((double)__uint_as_float(p.sc->bn2max));
-      double eps_dot = (double)p.c_rel * qn * bnmax;
-      double eps_cos = (double)p.c_rel * qn;
-      if (p.f16) {
-        // query elements below fp16's normal range after scaling are quantised to 2^-25
-        const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
-        const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
-        eps_dot += qquant * bnmax;
-        eps_cos += qquant;
-        if (p.direct) {
-          // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
-          // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
-          // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
-          const int sbg = direct_base_exp(1, p.metric, p.sc);
-          const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
-          eps_dot += bquant;
-          eps_cos += bquant + ldexp(1.0, -22) * qn;
-        }
+  // every lane evaluates the (warp-uniform) bound: cheaper than a broadcast of its five results
+  int fail = 0;
+  double eps = 0.0;
+  unsigned int thr_ord = 0, thr1_ord = 0;
+  if (!countable) {
+    fail = 1;
+  } else {
+    // proven bound on |approximate key - exact key| for this query (DESIGN.md "error bound")
+    const double qn = sqrt(qn2);
+    const double bnmax = sqrt((double)__uint_as_float(p.sc->bn2max));
+    double eps_dot = (double)p.c_rel * qn * bnmax;
+    double eps_cos = (double)p.c_rel * qn;
+    if (p.f16) {
+      // query elements below fp16's normal range after scaling are quantised to 2^-25
+      const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
+      const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
+      eps_dot += qquant * bnmax;
+      eps_cos += qquant;
+      if (p.direct) {
+        // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
+        // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
+        // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
+        const int sbg = direct_base_exp(1, p.metric, p.sc);
+        const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
+        eps_dot += bquant;
+        eps_cos += bquant + ldexp(1.0, -22) * qn;
       }
-      eps = eps_dot;
-      if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
-      else if (p.metric == NWK_METRIC_COSINE) eps = eps_cos;
-      const float key_k = ord2f(s_prefix);     // the k-th smallest approximate key
-      // + the fp32 rounding of alpha + beta*acc itself
-      eps += 3.0e-7 * fabs((double)key_k) + 1e-30;
-      const float thr = __double2float_ru((double)key_k + 2.0 * eps);
-      const float tau = p.tau[q];
-      if (!(thr < tau)) fail = 1;          // band reaches the logging threshold: cannot certify
-      thr_ord = f2ord(thr);
-      thr1_ord = f2ord(__double2float_ru((double)key_k + eps));
     }
-    s_fail = fail;
-    s_thr_ord = thr_ord;
-    s_thr1_ord = thr1_ord;
-    s_R = 0;
-    s_R2 = 0;
-    p.epsq[q] = (float)eps;
-    p.qn2[q] = qn2;
+    eps = eps_dot;
+    if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
+    else if (p.metric == NWK_METRIC_COSINE) eps = eps_cos;
+    const float key_k = ord2f(prefix);       // the k-th smallest approximate key
+    // + the fp32 rounding of alpha + beta*acc itself
+    eps += 3.0e-7 * fabs((double)key_k) + 1e-30;
+    const float thr = __double2float_ru((double)key_k + 2.0 * eps);
+    const float tau = p.tau[q];
+    if (!(thr < tau)) fail = 1;            // band reaches the logging threshold: cannot certify
+    thr_ord = f2ord(thr);
+    thr1_ord = f2ord(__double2float_ru((double)key_k + eps));
   }
-  __syncthreads();
 
   // Compact the records of the inner band (key <= a_k + eps) to the front of the query's log:
   // rerank_kernel recomputes exactly these.  Their exact k-th distance D_k bounds the true k-th
   // from above, so a row of the outer band (a_k + eps, a_k + 2 eps] can only matter when its
-  // key is <= D_k + eps; those records are parked at the end of the record half of the log
-  // (slots LOG_CAP/2-1 downwards) and output_kernel re-ranks the few that pass that test.
+  // key is <= D_k + eps; those records are parked at the very end of the log (slots LOG_CAP-1
+  // downwards; rerank_kernel's fp64 distances occupy [LOG_CAP/2, LOG_CAP/2 + R)) and
+  // output_kernel re-ranks the few that pass that test.  Two sweeps: count, then move in place
+  // (a record only ever moves to a slot the warp has already read).
   int R = 0, R2 = 0;
   if (countable) {
-    const unsigned int thr_ord = s_thr_ord, thr1_ord = s_thr1_ord;
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
-      const unsigned long long rec = s_log[i];
-      const unsigned int o = (unsigned int)(rec >> 32);
-      if (o <= thr1_ord) {
-        const int pos = atomicAdd(&s_R, 1);
-        if (pos < RERANK_MAX && !s_fail) glog[pos] = rec;
-      } else if (o <= thr_ord) {
-        const int pos = atomicAdd(&s_R2, 1);
-        if (pos < RERANK_MAX && !s_fail) glog[LOG_CAP / 2 - 1 - pos] = rec;
+    for (int i0 = 0; i0 < c; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned int o = i < c ? (unsigned int)(glog[i] >> 32) : 0xffffffffu;
+      R += __popc(__ballot_sync(0xffffffffu, i < c && o <= thr1_ord));
+      R2 += __popc(__ballot_sync(0xffffffffu, i < c && o > thr1_ord && o <= thr_ord));
+    }
+    // the two regions (and the distances) must not overlap, nor the outer band the unread records
+    if (R + R2 > RERANK_MAX || c + R2 > LOG_CAP) fail = 1;
+    if (!fail) {
+      int w1 = 0, w2 = 0;
+      const unsigned int lt = (1u << lane) - 1u;
+      for (int i0 = 0; i0 < c; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned long long rec = i < c ? glog[i] : 0xffffffffffffffffull;
+        const unsigned int o = (unsigned int)(rec >> 32);
+        const bool in1 = i < c && o <= thr1_ord;
+        const bool in2 = i < c && !in1 && o <= thr_ord;
+        const unsigned int b1 = __ballot_sync(0xffffffffu, in1), b2 = __ballot_sync(0xffffffffu, in2);
+        if (in1) glog[w1 + __popc(b1 & lt)] = rec;
+        if (in2) glog[LOG_CAP - 1 - (w2 + __popc(b2 & lt))] = rec;
+        w1 += __popc(b1);
+        w2 += __popc(b2);
+        __syncwarp();
       }
     }
-    __syncthreads();
-    R = s_R;
-    R2 = s_R2;
   }
-  if (threadIdx.x == 0) {
-    int fail = s_fail;
-    if (R + R2 > RERANK_MAX) { fail = 1; R = min(R, RERANK_MAX); }   // the two regions would overlap
+  if (lane == 0) {
+    p.epsq[q] = (float)eps;
+    p.qn2[q] = qn2;
     atomicAdd(p.sc->stat_sum + 0, (unsigned long long)total);
-    atomicAdd(p.sc->stat_sum + 1, (unsigned long long)R);
+    atomicAdd(p.sc->stat_sum + 1, (unsigned long long)min(R, RERANK_MAX));
     atomicMax(p.sc->stat_max + 0, total);
-    atomicMax(p.sc->stat_max + 1, (unsigned int)R);
+    atomicMax(p.sc->stat_max + 1, (unsigned int)min(R, RERANK_MAX));
     if (fail) {
       int slot = atomicAdd(&p.sc->fail_cnt, 1);
       p.fail_list[slot] = (int)q;
@@ -1314,7 +1313,7 @@ output_kernel(const FinParams p) {
     const double bound = (s_key[p.k - 1] - key_shift) * key_scale + eps;
     __syncthreads();                           // every thread has read s_key[k-1] before the tail is reused
     for (int i = threadIdx.x; i < R2; i += blockDim.x) {
-      const unsigned long long rec = glog[LOG_CAP / 2 - 1 - i];
+      const unsigned long long rec = glog[LOG_CAP - 1 - i];
       const float akey = ord2f((uint32_t)(rec >> 32));
       if ((double)akey <= bound) {
         const int pos = atomicAdd(&s_nx, 1);
@@ -1694,12 +1693,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
   f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   {
-    static bool sel_optin = false;
-    if (!sel_optin) {
-      NWK_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOG_CAP * 8));
-      sel_optin = true;
-    }
-    select_kernel<<<(unsigned)nq, SEL_THREADS, LOG_CAP * 8, s>>>(f);
+    select_kernel<<<(unsigned)((nq + SEL_THREADS / 32 - 1) / (SEL_THREADS / 32)), SEL_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();
     const int rr_smem = (d + 3) / 4 * 16;
     static int rr_optin = 48 * 1024;
