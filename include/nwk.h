@@ -138,6 +138,16 @@ int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq,
 typedef struct nwk_topk_state nwk_topk_state;
 int nwk_topk_state_create(int64_t nq, int32_t k, nwk_topk_state** out);
 int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* idx, void* stream);
+/* search() = "knn of one more slab of the base, folded into the state" in one call: what the
+ * loop body of cu_knn_ds.py:201-226 does with knn() + concat, made incremental.  The state's
+ * current k-th distances bound the search (a slab row can only enter the result if it beats the
+ * query's k-th best so far), so slabs after the first log and re-rank a fraction of the
+ * candidates; results are identical to update(knn(slab)).  base / query / workspace as for
+ * nwk_knn_f32 with nq and k taken from the state (nb >= k, workspace of
+ * nwk_knn_workspace_bytes(nb, nq, d, k, ...)); synchronises the stream like nwk_knn_f32. */
+int nwk_topk_state_search(nwk_topk_state* st, const float* base, int64_t nb, const float* query, int32_t d,
+                          int32_t metric, int64_t id_offset, void* workspace, size_t ws_bytes, uint32_t flags,
+                          nwk_knn_stats* stats, void* stream);
 int nwk_topk_state_finalize(nwk_topk_state* st, float* out_dist, int64_t* out_idx, void* stream);
 int nwk_topk_state_destroy(nwk_topk_state* st);
 

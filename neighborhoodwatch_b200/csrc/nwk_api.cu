@@ -20,7 +20,7 @@ bool tc_path_supported(long long nb, long long nq, int d, int k);
 size_t tc_workspace_bytes(long long nb, long long nq, int d, int k);
 int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
-           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s);
+           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s, const float* bound, long long bound_stride);
 int tc_debug_tile(const float* base, long long nb, const float* query, long long nq, int d, long long b0,
                   long long q0, float* out, int use_f16, cudaStream_t s);
 int synth_fill(float* out, long long rows, int d, unsigned long long seed, long long row0, int normalize,
@@ -131,9 +131,11 @@ size_t nwk_knn_workspace_bytes(int64_t nb, int64_t nq, int32_t d, int32_t k, int
   return exact_scan_workspace_bytes(nb, nq, k) + 256;
 }
 
-int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int32_t k,
-                int32_t metric, int64_t id_offset, float* out_dist, int64_t* out_idx, void* workspace,
-                size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats, void* stream) {
+// nwk_knn_f32, optionally bounded by the caller's current k-th distances (bound[q * bound_stride], device)
+static int knn_impl(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int32_t k,
+                    int32_t metric, int64_t id_offset, float* out_dist, int64_t* out_idx, void* workspace,
+                    size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats, void* stream, const float* bound,
+                    long long bound_stride) {
   if (!base || !query || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
   if (nb <= 0 || nq < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad shape nb=%lld nq=%lld d=%d", (long long)nb, (long long)nq, d);
   if (k <= 0 || k > NWK_MAX_K) return fail(NWK_ERR_ARG, "k=%d outside [1, %d]", k, NWK_MAX_K);
@@ -147,9 +149,12 @@ int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, i
     return fail(NWK_ERR_WORKSPACE, "workspace of %zu bytes is smaller than nwk_knn_workspace_bytes() = %zu",
                 ws_bytes, nwk_knn_workspace_bytes(nb, nq, d, k, metric, flags));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (want_tc(nb, nq, d, k, flags))
+  // (the tensor-core path reads rows as 16-byte vectors and through TMA)
+  const bool aligned = ((reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(query)) & 15u) == 0;
+  if (want_tc(nb, nq, d, k, flags) && aligned)
     return tc_knn(base, nb, query, nq, d, k, metric, id_offset, out_dist, (long long*)out_idx, workspace,
-                  ws_bytes, flags, stats, s);
+                  ws_bytes, flags, stats, s, bound, bound_stride);
+  // the fp64 scan ignores the bound: it returns the slab's full top-k, a superset of what the caller needs
   const long long l0 = g_launches.load();
   NWK_TRY(exact_scan(base, nb, query, d, k, metric, id_offset, nullptr, nq, out_dist, (long long*)out_idx,
                      workspace, ws_bytes, s));
@@ -159,6 +164,13 @@ int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, i
     stats->gpu_launches = (int)(g_launches.load() - l0);
   }
   return NWK_OK;
+}
+
+int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, int32_t k,
+                int32_t metric, int64_t id_offset, float* out_dist, int64_t* out_idx, void* workspace,
+                size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats, void* stream) {
+  return knn_impl(base, nb, query, nq, d, k, metric, id_offset, out_dist, out_idx, workspace, ws_bytes, flags, stats,
+                  stream, nullptr, 0);
 }
 
 size_t nwk_merge_workspace_bytes(int32_t P, int64_t nq, int32_t k_in, int32_t k_out) {
@@ -221,6 +233,21 @@ int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* 
   const size_t n = (size_t)st->nq * st->k;
   NWK_CUDA(cudaMemcpyAsync(st->pack_d + n, dist, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   NWK_CUDA(cudaMemcpyAsync(st->pack_i + n, idx, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  NWK_TRY(merge_topk(2, st->pack_d, st->pack_i, st->nq, st->k, st->k, st->tmp_d, st->tmp_i, st->ws, st->ws_bytes, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  return NWK_OK;
+}
+
+int nwk_topk_state_search(nwk_topk_state* st, const float* base, int64_t nb, const float* query, int32_t d,
+                          int32_t metric, int64_t id_offset, void* workspace, size_t ws_bytes, uint32_t flags,
+                          nwk_knn_stats* stats, void* stream) {
+  if (!st) return fail(NWK_ERR_ARG, "null pointer argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)st->nq * st->k;
+  // the slab's list goes straight into the incoming slot; the current k-th distances bound the search
+  NWK_TRY(knn_impl(base, nb, query, st->nq, d, st->k, metric, id_offset, st->pack_d + n, (int64_t*)(st->pack_i + n),
+                   workspace, ws_bytes, flags, stats, stream, st->pack_d + (st->k - 1), st->k));
   NWK_TRY(merge_topk(2, st->pack_d, st->pack_i, st->nq, st->k, st->k, st->tmp_d, st->tmp_i, st->ws, st->ws_bytes, s));
   NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
@@ -335,8 +362,12 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
       rc = [&]() -> int {
         NWK_CUDA(cudaStreamWaitEvent(c.comp_stream, c.copied[b], 0));
         nwk_knn_stats s1{};
-        NWK_TRY(nwk_knn_f32(c.slab[b], rows, c.query, nq, d, k, metric, id_offset + i * slab_rows, c.part_d,
-                            (int64_t*)c.part_i, c.ws, c.ws_bytes, flags, &s1, c.comp_stream));
+        if (st)
+          NWK_TRY(nwk_topk_state_search(st, c.slab[b], rows, c.query, d, metric, id_offset + i * slab_rows, c.ws,
+                                        c.ws_bytes, flags, &s1, c.comp_stream));
+        else
+          NWK_TRY(nwk_knn_f32(c.slab[b], rows, c.query, nq, d, k, metric, id_offset + i * slab_rows, c.part_d,
+                              (int64_t*)c.part_i, c.ws, c.ws_bytes, flags, &s1, c.comp_stream));
         NWK_CUDA(cudaEventRecord(c.freed[b], c.comp_stream));
         total.path = s1.path;
         total.n_fallback_queries += s1.n_fallback_queries;
@@ -346,7 +377,6 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
         if (s1.max_candidates > total.max_candidates) total.max_candidates = s1.max_candidates;
         if (s1.max_rerank > total.max_rerank) total.max_rerank = s1.max_rerank;
         if (s1.max_err_ratio > total.max_err_ratio) total.max_err_ratio = s1.max_err_ratio;
-        if (st) NWK_TRY(nwk_topk_state_update(st, c.part_d, (const int64_t*)c.part_i, c.comp_stream));
         return NWK_OK;
       }();
     }

@@ -966,6 +966,7 @@ struct FinParams {
   int f16;                     // fp16 operands: adds the subnormal-quantisation term
   int direct;                  // direct keys: one global base scale (base-side quantisation term, cosine pre-normalisation)
   const float* alpha;          // direct keys: +inf marks base rows that must never rank
+  const unsigned char* bflag;  // [nq] or null: 1 = the caller's distance bound lowered tau_q (nwk_topk_state_search)
   float* out_dist; long long* out_idx;
   int* fail_list;
 };
@@ -975,6 +976,66 @@ constexpr int RR_THREADS = 256;
 constexpr int RR_ROWS = 4;                       // candidate rows in flight per warp
 constexpr int RR_BLOCK_ROWS = (RR_THREADS / 32) * RR_ROWS;
 constexpr int OUT_THREADS = 128;
+
+// Proven bound on |approximate key - exact key| for one query (DESIGN.md "error bound"), without
+// the fp32 rounding of the key itself (3e-7 |key|, added by the callers for the key at hand).
+__device__ __forceinline__ double key_error_bound(const FinParams& p, double qn2) {
+  const double qn = sqrt(qn2);
+  const double bnmax = sqrt((double)__uint_as_float(p.sc->bn2max));
+  double eps_dot = (double)p.c_rel * qn * bnmax;
+  double eps_cos = (double)p.c_rel * qn;
+  if (p.f16) {
+    // query elements below fp16's normal range after scaling are quantised to 2^-25
+    const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
+    const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
+    eps_dot += qquant * bnmax;
+    eps_cos += qquant;
+    if (p.direct) {
+      // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
+      // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
+      // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
+      const int sbg = direct_base_exp(1, p.metric, p.sc);
+      const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
+      eps_dot += bquant;
+      eps_cos += bquant + ldexp(1.0, -22) * qn;
+    }
+  }
+  if (p.metric == NWK_METRIC_SQEUCLIDEAN) return 2.0 * eps_dot;
+  if (p.metric == NWK_METRIC_COSINE) return eps_cos;
+  return eps_dot;
+}
+
+// Running searches (nwk_topk_state_search): the caller already holds k neighbours of every query
+// from earlier slabs of the base; a row of this slab can only enter the result if its exact
+// distance is at most the query's current k-th best D.  In key units that is key(D) (the keys omit
+// the per-query constants), so rows with an approximate key >= key(D) + eps cannot matter and the
+// logging threshold drops to min(tau_q, that): later slabs log and re-rank a fraction of the
+// candidates of the first one.  One warp per query.
+__global__ void __launch_bounds__(256)
+tau_bound_kernel(const FinParams p, const float* __restrict__ bound, long long stride, float* __restrict__ tau,
+                 unsigned char* __restrict__ bflag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 8 + warp;
+  if (q >= p.nq) return;
+  double qn2 = 0.0;
+  const float* qrow = p.query + q * p.d;
+  for (int c2 = lane; c2 < p.d; c2 += 32) { const double v = qrow[c2]; qn2 = fma(v, v, qn2); }
+  qn2 = warp_sum(qn2);
+  if (lane != 0) return;
+  unsigned char flag = 0;
+  const float D = bound[q * stride];
+  if (D < __int_as_float(0x7f800000)) {
+    // D is the fp32 rounding of an exact distance: the true value is at most D + ulp(D)/2
+    const double d_up = (double)D + fabs((double)D) * 1.2e-7 + 1e-37;
+    const double key_shift = (p.metric == NWK_METRIC_SQEUCLIDEAN) ? qn2 : 1.0;
+    const double key_scale = (p.metric == NWK_METRIC_COSINE) ? sqrt(qn2) : 1.0;
+    const double kb = (d_up - key_shift) * key_scale;
+    const double eps = key_error_bound(p, qn2) + 3.0e-7 * fabs(kb) + 1e-30;
+    const float t = __double2float_ru(kb + 1.001 * eps);
+    if (t < tau[q]) { tau[q] = t; flag = 1; }
+  }
+  bflag[q] = flag;
+}
 
 // select: find the k-th smallest logged key a_k by radix select (4 passes of 8 bits over the
 // order-preserving 32-bit keys), form the band [a_k, a_k + 2 eps], certify, and compact the R
@@ -1054,42 +1115,26 @@ select_kernel(const FinParams p) {
   }
 
   // every lane evaluates the (warp-uniform) bound: cheaper than a broadcast of its five results
+  // A bounded query (running search, tau_q lowered to the caller's k-th distance): every row that
+  // can still enter the caller's result is in the log whatever the band looks like, and fewer than
+  // k rows may have passed at all -- then all of them are kept and the output is padded.
+  const bool bounded = p.bflag != nullptr && p.bflag[q] != 0;
+  const bool keep_all = bounded && total <= (unsigned int)LOG_CAP && c < p.k;
   int fail = 0;
-  double eps = 0.0;
+  double eps = key_error_bound(p, qn2) + 1e-30;
   unsigned int thr_ord = 0, thr1_ord = 0;
-  if (!countable) {
+  if (keep_all) {
+    thr_ord = thr1_ord = 0xff800000u;        // f2ord(+inf): every logged key (none is nan-ordered unless flagged)
+    eps += 3.0e-7 * fabs((double)p.tau[q]);
+  } else if (!countable) {
     fail = 1;
   } else {
-    // proven bound on |approximate key - exact key| for this query (DESIGN.md "error bound")
-    const double qn = sqrt(qn2);
-    const double bnmax = sqrt((double)__uint_as_float(p.sc->bn2max));
-    double eps_dot = (double)p.c_rel * qn * bnmax;
-    double eps_cos = (double)p.c_rel * qn;
-    if (p.f16) {
-      // query elements below fp16's normal range after scaling are quantised to 2^-25
-      const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
-      const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
-      eps_dot += qquant * bnmax;
-      eps_cos += qquant;
-      if (p.direct) {
-        // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
-        // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
-        // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
-        const int sbg = direct_base_exp(1, p.metric, p.sc);
-        const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
-        eps_dot += bquant;
-        eps_cos += bquant + ldexp(1.0, -22) * qn;
-      }
-    }
-    eps = eps_dot;
-    if (p.metric == NWK_METRIC_SQEUCLIDEAN) eps = 2.0 * eps_dot;
-    else if (p.metric == NWK_METRIC_COSINE) eps = eps_cos;
     const float key_k = ord2f(prefix);       // the k-th smallest approximate key
     // + the fp32 rounding of alpha + beta*acc itself
-    eps += 3.0e-7 * fabs((double)key_k) + 1e-30;
+    eps += 3.0e-7 * fabs((double)key_k);
     const float thr = __double2float_ru((double)key_k + 2.0 * eps);
     const float tau = p.tau[q];
-    if (!(thr < tau)) fail = 1;            // band reaches the logging threshold: cannot certify
+    if (!(thr < tau) && !bounded) fail = 1;  // band reaches the logging threshold: cannot certify
     thr_ord = f2ord(thr);
     thr1_ord = f2ord(__double2float_ru((double)key_k + eps));
   }
@@ -1102,7 +1147,7 @@ select_kernel(const FinParams p) {
   // output_kernel re-ranks the few that pass that test.  Two sweeps: count, then move in place
   // (a record only ever moves to a slot the warp has already read).
   int R = 0, R2 = 0;
-  if (countable) {
+  if (countable || keep_all) {
     for (int i0 = 0; i0 < c; i0 += 32) {
       const int i = i0 + lane;
       const unsigned int o = i < c ? (unsigned int)(glog[i] >> 32) : 0xffffffffu;
@@ -1273,10 +1318,18 @@ output_kernel(const FinParams p) {
   __shared__ int s_nx;
   const long long q = blockIdx.x;
   const int R = p.rr[q];
-  if (R <= 0) return;
+  if (R < 0) return;                           // uncertified: the exact scan writes this query's row
+  if (R == 0) {
+    // a bounded query none of whose rows in this slab can enter the caller's result
+    for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+      p.out_dist[q * p.k + j] = __int_as_float(0x7f800000);
+      p.out_idx[q * p.k + j] = -1;
+    }
+    return;
+  }
   const int R2 = p.rr2[q];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int r2 = max(next_pow2(R), 2);
+  int r2 = max(next_pow2(max(R, p.k)), 2);     // (a bounded query may hold fewer than k rows: padded with +inf / -1)
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const unsigned long long* glog = p.log + q * LOG_CAP;
   const double* gdist = reinterpret_cast<const double*>(p.log + q * LOG_CAP + LOG_CAP / 2);
@@ -1357,8 +1410,9 @@ output_kernel(const FinParams p) {
   if (lane == 0) s_ratio[warp] = ratio;
   __syncthreads();
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+    const bool pad = s_id[j] == 0x7fffffffffffffffLL;
     p.out_dist[q * p.k + j] = (float)s_key[j];
-    p.out_idx[q * p.k + j] = s_id[j] + p.id_offset;
+    p.out_idx[q * p.k + j] = pad ? -1 : s_id[j] + p.id_offset;
   }
   if (threadIdx.x == 0) {
     float r = 0.f;
@@ -1486,6 +1540,7 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
   bytes += align_up((size_t)nq * 4, 256) * 4;               // fail list, rows-to-rerank (two bands), eps
   bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
+  bytes += align_up((size_t)nq, 256);                       // bound flags
   bytes += align_up((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M * 4, 256);    // per-part sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
   bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
@@ -1509,7 +1564,7 @@ static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMa
 
 int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
-           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s) {
+           unsigned int flags, nwk_knn_stats* stats, cudaStream_t s, const float* bound, long long bound_stride) {
   NWK_TRY(tc_optin());
   const int sms = sm_count();
   const bool f16 = !(flags & NWK_FLAG_TF32);
@@ -1525,6 +1580,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   int* rr2 = ar.take<int>((size_t)nq);
   float* epsq = ar.take<float>((size_t)nq);
   double* qn2 = ar.take<double>((size_t)nq);
+  unsigned char* bflag = ar.take<unsigned char>((size_t)nq);
   float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M);
   __half* bh = ar.take<__half>((size_t)nb * pl.dh);
   __half* qh = ar.take<__half>((size_t)nq * pl.dh);
@@ -1633,6 +1689,22 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
     NWK_LAUNCH_CHECK();
   }
+  FinParams f{};
+  f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
+  f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
+  f.rr = rr; f.rr2 = rr2; f.epsq = epsq; f.qn2 = qn2; f.direct = direct ? 1 : 0; f.alpha = alpha;
+  f.bflag = bound ? bflag : nullptr;
+  // Relative error of acc against sum |q_i b_i| <= |q||b|:
+  //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
+  //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
+  // plus the fp32 accumulation inside the tensor core, budgeted at 4 ulp per MMA step.
+  const double steps = (double)d / (f16 ? 16.0 : 8.0) + 2.0;
+  f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
+  f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
+  if (bound) {
+    tau_bound_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(f, bound, bound_stride, tau, bflag);
+    NWK_LAUNCH_CHECK();
+  }
   if (profile) cudaEventRecord(ev[2], s);
   if (pair) {
     const int clusters = sms / 2;
@@ -1681,17 +1753,6 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     cudaFree(d_prof);
   }
 
-  FinParams f{};
-  f.base = base; f.query = query; f.nb = nb; f.nq = nq; f.d = d; f.k = k; f.metric = metric;
-  f.id_offset = id_offset; f.tau = tau; f.cnt = cnt; f.log = log; f.sc = sc; f.f16 = f16 ? 1 : 0;
-  f.rr = rr; f.rr2 = rr2; f.epsq = epsq; f.qn2 = qn2; f.direct = direct ? 1 : 0; f.alpha = alpha;
-  // Relative error of acc against sum |q_i b_i| <= |q||b|:
-  //   fp16 (round-to-nearest, 11-bit significand):  (1 + 2^-11)^2 - 1 per product
-  //   tf32 (the tensor core drops the low 13 bits): (1 + 2^-10)^2 - 1 per product
-  // plus the fp32 accumulation inside the tensor core, budgeted at 4 ulp per MMA step.
-  const double steps = (double)d / (f16 ? 16.0 : 8.0) + 2.0;
-  f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
-  f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   {
     select_kernel<<<(unsigned)((nq + SEL_THREADS / 32 - 1) / (SEL_THREADS / 32)), SEL_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();

@@ -230,11 +230,11 @@ def process_dataset_batches(data_dir,
         dataset = dev_cm[b][:, :rows].t().contiguous()
         if split:
             assert (k <= len(dataset))                              # cu_knn_ds.py:204
-        dist, idx = _knn.knn(dataset, queries, k, metric="sqeuclidean", id_offset=offset)
         if state is not None:
-            state.update(dist, idx)
+            # knn of this slab folded into the running result; the current k-th distances bound the search
+            state.search(dataset, queries, metric="sqeuclidean", id_offset=offset)
         else:
-            result = (dist, idx)
+            result = _knn.knn(dataset, queries, k, metric="sqeuclidean", id_offset=offset)
         lock.release()
     th.join()
     if error:

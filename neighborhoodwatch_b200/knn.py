@@ -139,6 +139,27 @@ class RunningTopK:
             # keep the inputs alive until the enqueued copies have run
             torch.cuda.current_stream(self.device).synchronize()
 
+    def search(self, dataset: torch.Tensor, queries: torch.Tensor, metric: str = "sqeuclidean", id_offset: int = 0,
+               profile: bool = False) -> None:
+        """knn(dataset slab) folded into the state in one call (nwk_topk_state_search): the current
+        k-th distances bound the search, so slabs after the first cost a fraction of the finish stage."""
+        global last_stats
+        dataset = _as_f32_cuda(dataset, "dataset")
+        queries = _as_f32_cuda(queries, "queries")
+        assert queries.shape[0] == self.nq and dataset.shape[1] == queries.shape[1]
+        assert self.k <= len(dataset), f"k={self.k} exceeds dataset rows {len(dataset)}"      # cu_knn_ds.py:204
+        metric_id = _native.METRIC_IDS[metric]
+        nb, d = dataset.shape
+        flags = _native.FLAG_PROFILE if profile else 0
+        with torch.cuda.device(self.device):
+            ws_bytes = self._lib.nwk_knn_workspace_bytes(nb, self.nq, d, self.k, metric_id, flags)
+            ws = _workspace(ws_bytes, self.device)
+            stats = _native.KnnStats()
+            _native.check(self._lib.nwk_topk_state_search(self._handle, dataset.data_ptr(), nb, queries.data_ptr(), d,
+                                                          metric_id, int(id_offset), ws.data_ptr(), ws.numel(), flags,
+                                                          ctypes.byref(stats), _stream_ptr(self.device)))
+            last_stats = stats.as_dict()
+
     def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
         with torch.cuda.device(self.device):
             out_d = torch.empty((self.nq, self.k), dtype=torch.float32, device=self.device)

@@ -264,6 +264,39 @@ def test_running_topk_equals_one_shot(cuda_device):
     st.close()
 
 
+@pytest.mark.parametrize("metric", ko.METRICS)
+@pytest.mark.parametrize("nb,slab,d,k,order", [
+    (6000, 1500, 64, 20, "as-is"),         # slabs small enough to be logged whole: the bound alone thins them out
+    (160000, 40000, 128, 100, "as-is"),    # sampled slabs; later slabs pass fewer than k rows for most queries
+    (160000, 40000, 128, 100, "far-first"),  # every slab holds nearer rows than the one before: the bound never bites
+    (90000, 30000, 768, 100, "near-first"),  # the first slab already holds most of the answer (CTA-pair filter)
+])
+def test_running_search_equals_one_shot(cuda_device, metric, nb, slab, d, k, order):
+    """nwk_topk_state_search (knn of a slab bounded by the state's k-th distances, folded into the
+    state) over all slabs == the oracle on the whole base, whatever the order the rows arrive in."""
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(nb, d, 1234)
+    q = synth.vectors(64, d, 5678)
+    if order != "as-is":
+        # sort the rows by distance to the mean query, so slabs differ systematically
+        key = ko.distances_f64(base, q.mean(axis=0, keepdims=True), metric)[0]
+        perm = np.argsort(key if order == "near-first" else -key, kind="stable")
+        base = np.ascontiguousarray(base[perm])
+    bd, qd = _dev(base, cuda_device), _dev(q, cuda_device)
+    st = knn.RunningTopK(len(q), k, cuda_device)
+    cands = []
+    for lo in range(0, nb, slab):
+        st.search(bd[lo:lo + slab], qd, metric=metric, id_offset=lo)
+        assert knn.last_stats["max_err_ratio"] <= 1.0, knn.last_stats
+        cands.append(knn.last_stats["total_candidates"])
+    rd, ri = st.result()
+    res = _check(rd, ri, base, q, k, metric)
+    st.close()
+    if order != "far-first":
+        assert cands[-1] < cands[0], cands           # the bound must actually thin out the later slabs
+    print(metric, (nb, slab, d, k, order), cands, res)
+
+
 def test_host_entry_point(cuda_device):
     from neighborhoodwatch_b200 import knn
     base = synth.vectors(30000, 128, 1234)
