@@ -68,8 +68,11 @@ constexpr int MASK_BYTES = (TB / 32) * TQ * 4;           // per-thread hit masks
 constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + AB_BYTES + APPEND_BYTES + MASK_BYTES + 256 + 1024;
 constexpr int SAMPLE_M = 32;                   // per-query sample list length (registers)
 constexpr int SAMPLE_WARM = 4;                 // warm-up: the 4 smallest of a part's first 4 chunks (128 sample rows) set the first threshold
-constexpr int SAMPLE_QCAP = (APPEND_BYTES + MASK_BYTES) / (TQ * 4);   // per-thread queue of admitted keys (shared memory)
+constexpr int SAMPLE_STAGES = 3;               // operand ring of the sample pass; the fourth stage's 48 KB hold the key queues
+constexpr int SAMPLE_WG = 2;                   // epilogue warpgroups of the sample pass, each with its own lists over half of the columns
+constexpr int SAMPLE_QCAP = STAGE_BYTES / (SAMPLE_WG * TQ * 4);       // per-thread queue of admitted keys (shared memory)
 constexpr int SAMPLE_MAX_PARTS = 8;            // parts a query tile's sample scan may be split into
+constexpr int SAMPLE_MAX_LISTS = SAMPLE_MAX_PARTS * SAMPLE_WG;        // lists per query that tau_merge_kernel unites
 static_assert(SAMPLE_QCAP >= 40, "the queue must take a whole 32-column chunk beyond the flush mark");
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
@@ -358,9 +361,9 @@ tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, float
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * 8 + warp;
   if (q >= nq) return;
-  uint32_t v[SAMPLE_MAX_PARTS];
+  uint32_t v[SAMPLE_MAX_LISTS];
 #pragma unroll
-  for (int i = 0; i < SAMPLE_MAX_PARTS; ++i)
+  for (int i = 0; i < SAMPLE_MAX_LISTS; ++i)
     v[i] = i < parts ? f2ord(slist[(q * parts + i) * SAMPLE_M + lane]) : 0xffffffffu;
   uint32_t ans = 0;
 #pragma unroll 1
@@ -368,7 +371,7 @@ tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, float
     const uint32_t trial = ans | (1u << bit);
     int below = 0;
 #pragma unroll
-    for (int i = 0; i < SAMPLE_MAX_PARTS; ++i) below += (v[i] < trial) ? 1 : 0;
+    for (int i = 0; i < SAMPLE_MAX_LISTS; ++i) below += (v[i] < trial) ? 1 : 0;
     below = __reduce_add_sync(0xffffffffu, below);
     if (below < SAMPLE_M) ans = trial;
   }
@@ -456,15 +459,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   static_assert(!ARES || (MODE == MODE_FILTER && F16 && !CTA2), "resident query tiles are built for the single-CTA fp16 filter pass");
   constexpr int BK = Op<F16>::BK;
   constexpr int UMMA_K = Op<F16>::UMMA_K;
-  constexpr int NST = CTA2 ? PAIR_STAGES : STAGES;
+  constexpr int NST = CTA2 ? PAIR_STAGES : (MODE == MODE_SAMPLE ? SAMPLE_STAGES : STAGES);
   constexpr int SB_BYTES = CTA2 ? STAGE_B_BYTES / 2 : STAGE_B_BYTES;   // base rows staged by this CTA
   constexpr int ST_BYTES = STAGE_A_BYTES + SB_BYTES;
-  static_assert(NST * ST_BYTES == STAGES * STAGE_BYTES, "both variants use the same 192 KB operand ring");
+  static_assert(NST * ST_BYTES == STAGES * STAGE_BYTES || MODE == MODE_SAMPLE, "the filter variants use the same 192 KB operand ring");
   using SchedT = Sched<MODE, CTA2>;
   const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;
   // the filter pass splits the 256 accumulator columns over two epilogue warpgroups; the sample
   // pass keeps one (its per-query list lives in one thread's registers)
-  constexpr int EPI_WG = (MODE == MODE_FILTER) ? 2 : 1;
+  constexpr int EPI_WG = (MODE == MODE_DUMP) ? 1 : 2;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   // (offset arithmetic on the __shared__ pointer keeps its address space: LDS/STS, not generic LD/ST)
@@ -502,8 +505,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], CTA2 ? 2 * 4 * EPI_WG
-                                          : (MODE == MODE_SAMPLE ? 4 : (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG));
+      ptx::mbar_init(&tempty_bar[a], CTA2 ? 2 * 4 * EPI_WG : (NWK_WARP_ARRIVE ? 4 : 128) * EPI_WG);
       ptx::mbar_init(&abfull_bar[a], 1);
       ptx::mbar_init(&abempty_bar[a], 4 * EPI_WG);
       ptx::mbar_init(&afull_bar[a], 1);
@@ -665,9 +667,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       __syncwarp();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (MODE == MODE_SAMPLE && warp >= 4 && warp < 8) {
-    // ===== sample epilogue: one warpgroup; thread <-> TMEM lane <-> query row of the tile.
-    // Each thread keeps the SAMPLE_M smallest keys of its part of the sample in registers.
+  } else if (MODE == MODE_SAMPLE && warp >= 4 && warp < 4 + 4 * SAMPLE_WG) {
+    // ===== sample epilogue: two warpgroups, each over half of every tile's columns;
+    // thread <-> TMEM lane <-> query row of the tile.  Each thread keeps the SAMPLE_M smallest
+    // keys of its half of its part of the sample in registers (tau_merge_kernel unites the lists).
     // Keys below the running threshold are only *queued* (one predicated shared-memory store
     // per element, no branches in the unrolled loop); the queue is merged into the list when
     // some lane's queue fills up, so a hit in one lane does not stall the other 31.  A part
@@ -675,8 +678,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
     // first threshold (about 3 % of the rows pass it), instead of 1000 full-length insertions.
     // Any threshold yields an exact result; the sample only steers the candidate count. =====
     const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
     const int row_in_tile = quad * 32 + lane;
-    float* s_queue = reinterpret_cast<float*>(s_app) + row_in_tile;       // slot i at s_queue[i * TQ]
+    constexpr int QSTRIDE = SAMPLE_WG * TQ;
+    constexpr int SCPW = (TB / 32) / SAMPLE_WG;      // 32-column chunks per warpgroup
+    // the key queues live in the 48 KB the sample pass's shorter operand ring leaves free
+    float* s_queue = reinterpret_cast<float*>(smem + SAMPLE_STAGES * STAGE_BYTES) + wg * TQ + row_in_tile;   // slot i at s_queue[i * QSTRIDE]
     Sched<MODE> sch(p);
     int qt, t; bool first, last;
     int acc = 0; uint32_t acc_phase = 0;
@@ -707,7 +714,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       auto flush = [&]() {
         const int maxc = __reduce_max_sync(0xffffffffu, cnt);
         for (int i = 0; i < maxc; ++i) {
-          const float key = (i < cnt) ? s_queue[i * TQ] : INF;
+          const float key = (i < cnt) ? s_queue[i * QSTRIDE] : INF;
 #pragma unroll
           for (int m = SAMPLE_M - 1; m > 0; --m) lst[m] = fmaxf(lst[m - 1], fminf(lst[m], key));
           lst[0] = fminf(lst[0], key);
@@ -740,21 +747,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
                                  fmaf(be.z, __uint_as_float(cur[4 * j4 + 2]), al.z), fmaf(be.w, __uint_as_float(cur[4 * j4 + 3]), al.w)};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (k4[e] < tau) { s_queue[cnt * TQ] = k4[e]; ++cnt; }
+              if (k4[e] < tau) { s_queue[cnt * QSTRIDE] = k4[e]; ++cnt; }
           }
           if (__any_sync(0xffffffffu, cnt > SAMPLE_QCAP - 32)) flush();
         }
       };
 
       uint32_t va[32], vb[32];
-      ptx::tmem_ld_32x32(taddr, va);
+      const int c0 = wg * SCPW;                      // first chunk of this warpgroup
+      ptx::tmem_ld_32x32(taddr + c0 * 32, va);
 #pragma unroll 1
-      for (int cp = 0; cp < TB / 32; cp += 2) {
+      for (int cp = c0; cp < c0 + SCPW; cp += 2) {
         ptx::tmem_wait_ld();
         ptx::tmem_ld_32x32(taddr + (cp + 1) * 32, vb);
         chunk(va, cp);
         ptx::tmem_wait_ld();
-        if (cp + 2 < TB / 32) ptx::tmem_ld_32x32(taddr + (cp + 2) * 32, va);
+        if (cp + 2 < c0 + SCPW) ptx::tmem_ld_32x32(taddr + (cp + 2) * 32, va);
         chunk(vb, cp + 1);
       }
       ptx::tmem_wait_ld();
@@ -767,7 +775,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
         if (q < p.nq) {
           // this CTA covered one part of the query tile's sample: publish its list, tau_merge_kernel
           // takes the SAMPLE_M-th smallest of the union
-          float* dst = p.slist + (q * sch.sParts + (sch.u % sch.sParts)) * SAMPLE_M;
+          float* dst = p.slist + (q * (sch.sParts * SAMPLE_WG) + (sch.u % sch.sParts) * SAMPLE_WG + wg) * SAMPLE_M;
 #pragma unroll
           for (int j = 0; j < SAMPLE_M; ++j) dst[j] = lst[j];
         }
@@ -1541,7 +1549,7 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)nq * 4, 256) * 4;               // fail list, rows-to-rerank (two bands), eps
   bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
   bytes += align_up((size_t)nq, 256);                       // bound flags
-  bytes += align_up((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M * 4, 256);    // per-part sample lists
+  bytes += align_up((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M * 4, 256);    // per-part, per-warpgroup sample lists
   bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
   bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
   bytes += align_up((size_t)pl.ns_pad * 4, 256) * 2;        // sample alpha, beta
@@ -1581,7 +1589,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   float* epsq = ar.take<float>((size_t)nq);
   double* qn2 = ar.take<double>((size_t)nq);
   unsigned char* bflag = ar.take<unsigned char>((size_t)nq);
-  float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_PARTS * SAMPLE_M);
+  float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M);
   __half* bh = ar.take<__half>((size_t)nb * pl.dh);
   __half* qh = ar.take<__half>((size_t)nq * pl.dh);
   float* salpha = ar.take<float>((size_t)pl.ns_pad);
@@ -1668,7 +1676,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   }
 
   if (pl.sample) {
-    fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_M, HUGE_VALF);
+    fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_WG * SAMPLE_M, HUGE_VALF);
     NWK_LAUNCH_CHECK();
     // the sample pass scans the compact matrix of sampled rows with their own alpha / beta
     CUtensorMap tm_s;
@@ -1683,7 +1691,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     ps.sWarm = pl.ns >= 8192 ? 1 : 0;
     int grid = pl.sParts * pl.nQT < sms ? pl.sParts * pl.nQT : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s));
-    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, pl.sParts, tau);
+    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, pl.sParts * SAMPLE_WG, tau);
     NWK_LAUNCH_CHECK();
   } else {
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
