@@ -1604,11 +1604,14 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   // Filter variant.  CTA pairs (cta_group::2) when the query tiles pair up without much waste and
   // the MMAs of a tile outlast its epilogue (measured: -6 % filter time at d = 768, -10 % at
   // d = 1536, but +25 % at d = 128, where the epilogue is the limit and the pair couples two of
-  // them).  Direct keys (no alpha / beta in the epilogue) where the epilogue is the limit: short
-  // rows; dot and cosine only (sq-L2 needs the per-row |b|^2 term).
+  // them).  Direct keys (no alpha / beta in the epilogue): dot and cosine only (sq-L2 needs the
+  // per-row |b|^2 term).
   bool pair = f16 && sms >= 2 && d >= 512 && (pl.nQT % 2 == 0 || pl.nQT >= 8);
   if (const char* e = getenv("NWK_PAIR")) pair = f16 && sms >= 2 && atoi(e) != 0;   // experiment switch
-  bool direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && pl.dh <= 256;
+  // (cosine rows are normalised in the same pass, so its direct keys cost nothing extra and pay at
+  //  any d: -6 % filter time at d = 768 under the power cap; dot needs one more read of the base
+  //  for the global scale, which only short rows win back)
+  bool direct = f16 && (metric == NWK_METRIC_COSINE || (metric == NWK_METRIC_DOT && pl.dh <= 256));
   if (const char* e = getenv("NWK_DIRECT")) direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && atoi(e) != 0;
   // resident query tiles: single-CTA filter, rows of at most 6 K-blocks (d <= 384)
   bool ares = f16 && !pair && pl.nKB <= 6;

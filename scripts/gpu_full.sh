@@ -7,5 +7,5 @@ PT="python -m pytest -q -m gpu --timeout 600 -p no:cacheprovider"
 run t_gpu $PT tests
 run smoke python __graft_entry__.py smoke
 run bench_c2 python bench.py --workload c2 --steps 20 --warmup 3
-for w in c1 c3shard c5shard; do run bench_$w python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e; done
+for w in c1 c3shard c5shard c4slab; do run bench_$w python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e; done
 bash scripts/gpu_ncu.sh c2
