@@ -1669,14 +1669,18 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
   p.sc = sc; p.metric = metric;
+  unsigned long long* d_prof = nullptr;
+#ifdef NWK_EXPERIMENTS
+  // timing experiments (scripts/gpu_exp.sh builds libnwk_exp.so with -DNWK_EXPERIMENTS); the
+  // product library does not read these switches: NWK_DEBUG_EPI makes the results wrong
   if (const char* e = getenv("NWK_DEBUG_EPI")) p.dbg = atoi(e);
   if (const char* e = getenv("NWK_DEBUG_NA")) p.dbg_na = atoi(e);
-  unsigned long long* d_prof = nullptr;
   if (getenv("NWK_DEBUG_PROF")) {
     NWK_CUDA(cudaMalloc(&d_prof, (size_t)sms * 4 * 8));
     NWK_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)sms * 4 * 8, s));
     p.prof = d_prof;
   }
+#endif
 
   if (pl.sample) {
     fill_f32_kernel<<<64, 256, 0, s>>>(slist, nq * pl.sParts * SAMPLE_WG * SAMPLE_M, HUGE_VALF);
