@@ -365,6 +365,29 @@ def test_large_shape_properties(cuda_device):
     print(st)
 
 
+@pytest.mark.parametrize("metric,d", [("dot", 128), ("sqeuclidean", 128), ("dot", 384)])
+def test_short_row_shapes_against_the_fp64_scan(cuda_device, metric, d):
+    """BASELINE config-5 / config-1 arithmetic (short rows: resident query tile, direct keys for dot)
+    at a size with many query tiles and sample parts: sampled queries must equal the on-device fp64
+    scan bit for bit, all rows must be ascending and free of repeats."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    nq, nb, k = 4000, 600_000, 100
+    bd = synth.device_vectors(nb, d, 1234, device=cuda_device)
+    qd = synth.device_vectors(nq, d, 5678, device=cuda_device)
+    got_d, got_i = knn.knn(bd, qd, k, metric=metric, id_offset=7)
+    st = dict(knn.last_stats)
+    assert st["path"] == 1 and st["max_err_ratio"] <= 1.0, st
+    assert st["n_fallback_queries"] <= nq // 100, st
+    assert torch.all(got_d[:, 1:] >= got_d[:, :-1])
+    srt = torch.sort(got_i, dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1])
+    sel = torch.arange(0, nq, 40, device=cuda_device)                     # 100 sampled queries
+    ex_d, ex_i = knn.knn(bd, qd[sel], k, metric=metric, id_offset=7, force_exact_scan=True)
+    assert torch.equal(ex_i, got_i[sel]) and torch.equal(ex_d, got_d[sel])
+    print(metric, d, st)
+
+
 def test_post_validator_reference_rule(cuda_device):
     """parquet_to_format.py:351-383: isclose(1 - dot, distance / 2) for every returned pair."""
     import torch
