@@ -44,6 +44,7 @@ WORKLOADS = {
     "c3shard": (10_000, 1_250_000, 1536, 100, "sqeuclidean"),     # one GPU's share of config 3 at W=8
     "c5shard": (32_000, 2_250_000, 128, 100, "dot"),              # one GPU's share of config 5 at W=8
     "c4slab": (100_000, 1_000_000, 1024, 100, "sqeuclidean"),     # one streamed slab of config 4 (12.5 such slabs per GPU at W=8)
+    "c5l2": (32_000, 2_250_000, 128, 100, "sqeuclidean"),         # the config-5 shard shape under the reference's default metric
     "tiny": (512, 50_000, 128, 100, "cosine"),
 }
 

@@ -61,6 +61,7 @@ typedef enum nwk_metric {
 #define NWK_FLAG_NO_FALLBACK      0x2u /* do not run the fp64 scan for uncertified queries (diagnostics) */
 #define NWK_FLAG_PROFILE          0x4u /* bracket each stage with CUDA events on `stream`; fills stats->ms_*  */
 #define NWK_FLAG_TF32             0x8u /* candidate stage on fp32 operands as TF32 (no fp16 staging copy)      */
+#define NWK_FLAG_ALPHA_BETA      0x10u /* candidate keys as alpha_j + beta_j * acc for every metric (no direct keys) */
 
 /* Per-call diagnostics (all counters refer to the last nwk_knn_f32 call they were passed to). */
 typedef struct nwk_knn_stats {

@@ -95,6 +95,7 @@ template <bool F16> struct Op {
 struct Scalars;
 struct TcParams {
   int nKB;
+  int kLast;                // MMA K-steps of the last K-block (the row pitch need not fill it; TMA zero-fills the rest)
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
@@ -124,6 +125,8 @@ struct Scalars {            // one block of device scalars, zeroed per call
   unsigned int stat_max[2];
   unsigned int err_ratio;   // max |approx key - exact key| / eps over re-ranked rows (float bits)
   unsigned int babsmax;     // max finite |b_ij| (float bits): the global base scale of the direct-key filter
+  unsigned int qn2max;      // max |q|^2 (float bits): the common scale of direct squared-L2 keys
+  int overflow;             // direct squared-L2 keys: some base row does not fit the scale taken from the queries
   unsigned long long stat_sum[2];
 };
 
@@ -159,16 +162,42 @@ __device__ __forceinline__ int f16_scale_exp(float maxabs) {
 }
 
 __device__ __forceinline__ float pow2f(int e);
+__device__ __forceinline__ void direct_exps(int metric, const Scalars* sc, int& sq, int& sb);
+
+// max |q|^2 over the queries (one warp per row); only direct squared-L2 keys need it
 __global__ void __launch_bounds__(256)
-qprep_kernel(const float* __restrict__ q, long long nq, int d, int dh, const Scalars* __restrict__ sc,
-             __half* __restrict__ qh) {
-  const int s = f16_scale_exp(__uint_as_float(sc->qabsmax));
-  const long long n = nq * dh;
+qnorm_kernel(const float* __restrict__ q, long long nq, int d, unsigned int* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = 0.f;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < nq; r += (long long)gridDim.x * 8) {
+    float a = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = q[r * d + c]; a = fmaf(v, v, a); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (a < __int_as_float(0x7f800000)) m = fmaxf(m, a);
+  }
+  if (lane == 0 && m > 0.f) atomicMax(out, __float_as_uint(m * 1.0001f));   // (fp32 summation slack)
+}
+
+// Direct squared-L2 keys put the -|b|^2/2 term of the key into the GEMM: the operand copies get
+// L2X_COLS extra K columns, the queries hold the powers of two L2X_Q there and every base row
+// three fp16 pieces h1, h2, h3 of X = 2^(2s-1) |b|^2 with h1 2^15 + h2 2^4 + h3 2^-7 = X (to 2^-29
+// relative), negated, so that acc' = 2^2s (q.b - |b|^2/2) and key = -2^(1-2s) acc'.
+constexpr int L2X_COLS = 8;
+__device__ __forceinline__ float l2x_q(int c) { return c == 0 ? 32768.f : (c == 1 ? 16.f : (c == 2 ? 0.0078125f : 0.f)); }
+
+__global__ void __launch_bounds__(256)
+qprep_kernel(const float* __restrict__ q, long long nq, int d, int dh, int pitch, int metric, int direct,
+             const Scalars* __restrict__ sc, __half* __restrict__ qh) {
+  int s = f16_scale_exp(__uint_as_float(sc->qabsmax)), sb_unused;
+  if (direct) direct_exps(metric, sc, s, sb_unused);
+  const long long n = nq * pitch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / dh;
-    int c = (int)(i - r * dh);
-    float v = c < d ? q[r * d + c] : 0.f;
-    qh[i] = __float2half_rn(v * pow2f(s));
+    long long r = i / pitch;
+    int c = (int)(i - r * pitch);
+    float v = c < d ? q[r * d + c] * pow2f(s) : 0.f;
+    if (c >= dh) v = (direct && metric == NWK_METRIC_SQEUCLIDEAN) ? l2x_q(c - dh) : 0.f;   // the |b|^2 columns' partners; padding
+    qh[i] = __float2half_rn(v);
   }
 }
 
@@ -182,14 +211,34 @@ __device__ __forceinline__ float pow2f(int e) {
 // 2^sbg (after normalisation to unit length for cosine), so the accumulator orders the rows by
 // itself: key = kscale * acc with kscale = -2^-(sq + sbg).  The filter epilogue then needs no
 // per-column alpha / beta at all (their shared-memory reads bound the general epilogue).
+//
+// Squared L2 (any d): queries and base share one scale 2^s taken from the largest query norm
+// (|q|_max 2^s in [2^12, 2^13)), because the |b|^2 term rides along as extra K columns whose
+// pieces must fit fp16: X = 2^(2s-1) |b|^2 <= 2^30.9, i.e. |b| <= 11 |q|_max.  No pass over the base
+// is needed for that scale; a base row that does not fit raises Scalars::overflow and the host
+// repeats the call with alpha / beta keys (embeddings of one model never do).
+__device__ __forceinline__ void direct_exps(int metric, const Scalars* sc, int& sq, int& sb) {
+  if (metric == NWK_METRIC_SQEUCLIDEAN) {
+    const float qn = sqrtf(__uint_as_float(sc->qn2max));
+    int e = 13;
+    if (qn > 0.f) frexpf(qn, &e);                      // qn = m 2^e, m in [0.5, 1)
+    sq = sb = max(-60, min(60, 13 - e));
+    return;
+  }
+  sq = f16_scale_exp(__uint_as_float(sc->qabsmax));
+  sb = (metric == NWK_METRIC_COSINE) ? 14              // unit rows: |element| <= 1 -> <= 2^14
+                                     : f16_scale_exp(__uint_as_float(sc->babsmax));
+}
 __device__ __forceinline__ int direct_base_exp(int direct, int metric, const Scalars* sc) {
   if (!direct) return 0;
-  if (metric == NWK_METRIC_COSINE) return 14;          // unit rows: |element| <= 1 -> <= 2^14
-  return f16_scale_exp(__uint_as_float(sc->babsmax));
+  int sq, sb;
+  direct_exps(metric, sc, sq, sb);
+  return sb;
 }
 __device__ __forceinline__ float direct_kscale(int metric, const Scalars* sc) {
-  const int sq = f16_scale_exp(__uint_as_float(sc->qabsmax));
-  return -pow2f(-(sq + direct_base_exp(1, metric, sc)));
+  int sq, sb;
+  direct_exps(metric, sc, sq, sb);
+  return metric == NWK_METRIC_SQEUCLIDEAN ? -pow2f(1 - (sq + sb)) : -pow2f(-(sq + sb));
 }
 
 // one warp per base row: |b|^2 (fp64), alpha/beta, optional fp16 copy with a per-row scale.
@@ -221,7 +270,8 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
                 float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
-                __half* __restrict__ bh, const SampleOut so, const int direct) {
+                __half* __restrict__ bh, const SampleOut so, const int direct, const int pitch) {
+  // pitch = elements per row of the fp16 copies: dh, or dh + L2X_COLS for direct squared-L2 keys
   constexpr int ROW_CACHE = 8;
   if (so.stride_log2 >= 0) {
     const float PINF = __int_as_float(0x7f800000);
@@ -233,9 +283,11 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float INF = __int_as_float(0x7f800000);
-  const int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
+  int sq = F16 ? f16_scale_exp(__uint_as_float(sc->qabsmax)) : 0;
   // direct keys (F16 only): every row shares one scale, so key = kscale * acc for the whole call
-  const int sbg = direct_base_exp(direct, metric, sc);
+  int sbg = 0;
+  if (direct) direct_exps(metric, sc, sq, sbg);
+  const bool l2x = direct && metric == NWK_METRIC_SQEUCLIDEAN;
   float local_max = 0.f;
   for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
     if (row >= nb) {
@@ -298,13 +350,35 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         // by alpha = +inf; the filter's slow path adds alpha to the key of every hit.  (Rows with
         // infinite entries keep them: their accumulators come out +-inf / nan like their distances.)
         row_ok = (a == a) && (metric != NWK_METRIC_COSINE || a > 0.0);
+        if (l2x && row_ok && !(ldexp(a, 2 * sbg - 1) <= 2.0e9)) {
+          // |b|^2 does not fit the scale taken from the queries: the host repeats the call with alpha / beta keys
+          row_ok = false;
+          if (lane == 0) sc->overflow = 1;
+        }
         sb = sbg;
         scale = pow2f(sbg);
         if (metric == NWK_METRIC_COSINE) scale = (float)(1.0 / sqrt(a)) * scale;   // unit row at 2^sbg
         if (!row_ok) scale = 0.f;
       }
-      __half* hrow = bh + row * dh;
-      __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * dh : nullptr;
+      __half* hrow = bh + row * pitch;
+      __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * pitch : nullptr;
+      if (l2x && lane == 0) {
+        // X = 2^(2s-1) |b|^2 as three fp16 pieces against the queries' 2^15, 2^4, 2^-7 (exact residuals in fp64)
+        float h1 = 0.f, h2 = 0.f, h3 = 0.f;
+        if (row_ok) {
+          const double X = ldexp(a, 2 * sbg - 1);
+          h1 = __half2float(__float2half_rn((float)(X * (1.0 / 32768.0))));
+          const double r1 = X - (double)h1 * 32768.0;
+          h2 = __half2float(__float2half_rn((float)(r1 * (1.0 / 16.0))));
+          const double r2 = r1 - (double)h2 * 16.0;
+          h3 = __half2float(__float2half_rn((float)(r2 * 128.0)));
+        }
+        __half2 p01 = __floats2half2_rn(-h1, -h2);
+        __half2 p23 = __floats2half2_rn(-h3, 0.f);
+        uint4 pk4 = make_uint4(*reinterpret_cast<unsigned int*>(&p01), *reinterpret_cast<unsigned int*>(&p23), 0u, 0u);
+        *reinterpret_cast<uint4*>(hrow + dh) = pk4;
+        if (hsrow) *reinterpret_cast<uint4*>(hsrow + dh) = pk4;
+      }
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
         const int c = lane * 4 + i * 128;
@@ -339,6 +413,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       float al = 0.f, be = -unscale;
       if (direct) {
         // be is the same for every row (direct_kscale); al only flags rows that must never rank
+        if (l2x) be = -pow2f(1 - (sq + sb));
         if (!row_ok) { al = INF; be = 0.f; }
       } else if (metric == NWK_METRIC_SQEUCLIDEAN) { al = (float)a; be = -2.f * unscale; }
       else if (metric == NWK_METRIC_COSINE) {
@@ -620,8 +695,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
                                      : ptx::smem_u32(smem + stage * ST_BYTES);
             const uint64_t da = ptx::umma_desc_sw128(sa);
             const uint64_t db = ptx::umma_desc_sw128(ARES ? ptx::smem_u32(b_ring + stage * STAGE_B_BYTES) : sa + STAGE_A_BYTES);
+            const int nk = (kb == p.nKB - 1) ? p.kLast : BK / UMMA_K;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= nk) break;
               // one MMA consumes 32 bytes of K inside the 128 B swizzle span: +2 in 16-byte units
               if (CTA2) ptx::mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
               else if (F16) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -971,6 +1048,7 @@ struct FinParams {
   double* qn2;                 // [nq] |q|^2
   Scalars* sc;
   float c_rel;                 // relative error constant of the operand format
+  float c_acc;                 // its accumulation part alone: 4 ulp(fp32) per MMA step
   int f16;                     // fp16 operands: adds the subnormal-quantisation term
   int direct;                  // direct keys: one global base scale (base-side quantisation term, cosine pre-normalisation)
   const float* alpha;          // direct keys: +inf marks base rows that must never rank
@@ -994,7 +1072,8 @@ __device__ __forceinline__ double key_error_bound(const FinParams& p, double qn2
   double eps_cos = (double)p.c_rel * qn;
   if (p.f16) {
     // query elements below fp16's normal range after scaling are quantised to 2^-25
-    const int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax));
+    int sq = f16_scale_exp(__uint_as_float(p.sc->qabsmax)), sbg = 0;
+    if (p.direct) direct_exps(p.metric, p.sc, sq, sbg);
     const double qquant = ldexp(1.0, -25 - sq) * sqrt((double)p.d);
     eps_dot += qquant * bnmax;
     eps_cos += qquant;
@@ -1002,10 +1081,13 @@ __device__ __forceinline__ double key_error_bound(const FinParams& p, double qn2
       // one scale 2^sbg for the whole base: elements below 2^-14 after scaling are quantised
       // to 2^-25 (scaled units), sum_i |q_i| 2^-25 2^-sbg <= sqrt(d) |q| 2^(-25 - sbg); cosine
       // rows were normalised in fp32 first (two roundings: 2^-23 relative per element)
-      const int sbg = direct_base_exp(1, p.metric, p.sc);
       const double bquant = ldexp(1.0, -25 - sbg) * sqrt((double)p.d) * qn;
       eps_dot += bquant;
       eps_cos += bquant + ldexp(1.0, -22) * qn;
+      // squared L2: |b|^2/2 is accumulated by the tensor core too (same 4-ulp budget per MMA step,
+      // one more step) and its three fp16 pieces leave 2^-28 of it
+      if (p.metric == NWK_METRIC_SQEUCLIDEAN)
+        eps_dot += ((double)p.c_acc + ldexp(1.0, -28)) * 0.5 * bnmax * bnmax + (double)p.c_acc * qn * bnmax;
     }
   }
   if (p.metric == NWK_METRIC_SQEUCLIDEAN) return 2.0 * eps_dot;
@@ -1453,12 +1535,13 @@ static int get_encode_fn(EncodeTiledFn* out) {
 
 // 2-D row-major operand [rows, row_elems] (elements of 4 or 2 bytes); box = 128 bytes x box_rows
 static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long row_elems, bool f16,
-                     int box_rows) {
+                     int box_rows, long long pitch_elems = 0) {
   EncodeTiledFn enc;
   NWK_TRY(get_encode_fn(&enc));
   const int esz = f16 ? 2 : 4;
+  if (pitch_elems <= 0) pitch_elems = row_elems;     // columns in [row_elems, pitch) are never read: TMA zero-fills them
   cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
@@ -1494,20 +1577,27 @@ bool tc_path_supported(long long nb, long long nq, int d, int k) {
 }
 
 struct TcPlan {
-  int nQT, nT, nKB, G, nChunks, nUnits, nS, sChunks, sParts, dh;
+  int nQT, nT, nKB, kLast, G, nChunks, nUnits, nS, sChunks, sParts, dh, kcols, pitch;
   bool sample;
   long long nb_pad, nq_pad;
   long long s_stride, ns, ns_pad;
 };
 
-static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16) {
+// xcols = extra K columns of the fp16 operand copies (L2X_COLS for direct squared-L2 keys)
+static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16, int xcols = 0) {
   (void)k;
   TcPlan pl{};
   const int bk = f16 ? 64 : 32;
   pl.dh = (d + 7) / 8 * 8;
+  // rows of the fp16 copies start on 128-byte lines (a box row that straddles two lines doubles the
+  // L2 -> SM requests: measured +50 % filter time at d = 1536 with a pitch of 1544)
+  pl.kcols = f16 ? pl.dh + xcols : d;                // row elements the MMAs have to cover
+  pl.pitch = f16 ? (pl.kcols + 63) / 64 * 64 : d;
   pl.nQT = (int)((nq + TQ - 1) / TQ);
   pl.nT = (int)((nb + TB - 1) / TB);
-  pl.nKB = (d + bk - 1) / bk;
+  const int kcols = pl.kcols;
+  pl.nKB = (kcols + bk - 1) / bk;
+  pl.kLast = (kcols - (pl.nKB - 1) * bk + (f16 ? 15 : 7)) / (f16 ? 16 : 8);
   pl.nb_pad = (long long)pl.nT * TB;
   pl.nq_pad = (long long)pl.nQT * TQ;
   long long pairs = (long long)pl.nQT * pl.nT;
@@ -1540,7 +1630,7 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
 }
 
 size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
-  TcPlan pl = make_plan(nb, nq, d, k, 148, true);
+  TcPlan pl = make_plan(nb, nq, d, k, 148, true, L2X_COLS);
   size_t bytes = 0;
   bytes += align_up((size_t)pl.nb_pad * 4, 256) * 2;        // alpha, beta
   bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
@@ -1550,10 +1640,10 @@ size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
   bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
   bytes += align_up((size_t)nq, 256);                       // bound flags
   bytes += align_up((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M * 4, 256);    // per-part, per-warpgroup sample lists
-  bytes += align_up((size_t)nb * pl.dh * 2, 256);           // fp16 base
-  bytes += align_up((size_t)nq * pl.dh * 2, 256);           // fp16 queries
+  bytes += align_up((size_t)nb * pl.pitch * 2, 256);        // fp16 base
+  bytes += align_up((size_t)nq * pl.pitch * 2, 256);        // fp16 queries
   bytes += align_up((size_t)pl.ns_pad * 4, 256) * 2;        // sample alpha, beta
-  bytes += align_up((size_t)(pl.ns + 1) * (size_t)(d > pl.dh ? d : pl.dh) * 4, 256);   // sample rows (fp16 or fp32)
+  bytes += align_up((size_t)(pl.ns + 1) * (size_t)(d > pl.pitch ? d : pl.pitch) * 4, 256);   // sample rows (fp16 or fp32)
   bytes += 4096;                                            // scalars
   // fallback scan for up to 64 queries is always provisioned; more is handled in rounds
   bytes += exact_scan_workspace_bytes(nb, 64, k) + 256;
@@ -1576,7 +1666,17 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   NWK_TRY(tc_optin());
   const int sms = sm_count();
   const bool f16 = !(flags & NWK_FLAG_TF32);
-  TcPlan pl = make_plan(nb, nq, d, k, sms, f16);
+  // Direct keys (no alpha / beta in the epilogue).  Cosine rows are normalised in the preparation
+  // pass anyway, so its direct keys cost nothing extra and pay at any d (-6 % filter time at
+  // d = 768 under the power cap).  Dot needs one more read of the base for the global scale, and
+  // squared L2 carries |b|^2 in L2X_COLS extra K columns = one more K-block per tile (with a scale
+  // taken from the queries; NWK_FLAG_ALPHA_BETA is the repeat after a scale overflow): both only
+  // pay for short rows, where the epilogue is the limit (measured for squared L2: -7.5 % per step
+  // at d = 128, +1.5 % at d = 1536).
+  bool direct = f16 && !(flags & NWK_FLAG_ALPHA_BETA) && (metric == NWK_METRIC_COSINE || (d + 7) / 8 * 8 <= 256);
+  if (const char* e = getenv("NWK_DIRECT")) direct = f16 && !(flags & NWK_FLAG_ALPHA_BETA) && atoi(e) != 0;   // experiment switch
+  const bool l2x = direct && metric == NWK_METRIC_SQEUCLIDEAN;
+  TcPlan pl = make_plan(nb, nq, d, k, sms, f16, l2x ? L2X_COLS : 0);
   Arena ar(ws, ws_bytes);
   float* alpha = ar.take<float>((size_t)pl.nb_pad);
   float* beta = ar.take<float>((size_t)pl.nb_pad);
@@ -1590,11 +1690,11 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   double* qn2 = ar.take<double>((size_t)nq);
   unsigned char* bflag = ar.take<unsigned char>((size_t)nq);
   float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M);
-  __half* bh = ar.take<__half>((size_t)nb * pl.dh);
-  __half* qh = ar.take<__half>((size_t)nq * pl.dh);
+  __half* bh = ar.take<__half>((size_t)nb * pl.pitch);
+  __half* qh = ar.take<__half>((size_t)nq * pl.pitch);
   float* salpha = ar.take<float>((size_t)pl.ns_pad);
   float* sbeta = ar.take<float>((size_t)pl.ns_pad);
-  float* srows = ar.take<float>((size_t)(pl.ns + 1) * (size_t)(d > pl.dh ? d : pl.dh));
+  float* srows = ar.take<float>((size_t)(pl.ns + 1) * (size_t)(d > pl.pitch ? d : pl.pitch));
   Scalars* sc = ar.take<Scalars>(1);
   ar.off = align_up(ar.off, 256);
   void* scan_ws = ar.base + ar.off;
@@ -1604,15 +1704,9 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   // Filter variant.  CTA pairs (cta_group::2) when the query tiles pair up without much waste and
   // the MMAs of a tile outlast its epilogue (measured: -6 % filter time at d = 768, -10 % at
   // d = 1536, but +25 % at d = 128, where the epilogue is the limit and the pair couples two of
-  // them).  Direct keys (no alpha / beta in the epilogue): dot and cosine only (sq-L2 needs the
-  // per-row |b|^2 term).
+  // them).
   bool pair = f16 && sms >= 2 && d >= 512 && (pl.nQT % 2 == 0 || pl.nQT >= 8);
   if (const char* e = getenv("NWK_PAIR")) pair = f16 && sms >= 2 && atoi(e) != 0;   // experiment switch
-  // (cosine rows are normalised in the same pass, so its direct keys cost nothing extra and pay at
-  //  any d: -6 % filter time at d = 768 under the power cap; dot needs one more read of the base
-  //  for the global scale, which only short rows win back)
-  bool direct = f16 && (metric == NWK_METRIC_COSINE || (metric == NWK_METRIC_DOT && pl.dh <= 256));
-  if (const char* e = getenv("NWK_DIRECT")) direct = f16 && metric != NWK_METRIC_SQEUCLIDEAN && atoi(e) != 0;
   // resident query tiles: single-CTA filter, rows of at most 6 K-blocks (d <= 384)
   bool ares = f16 && !pair && pl.nKB <= 6;
   if (const char* e = getenv("NWK_ARES")) ares = f16 && !pair && pl.nKB <= 6 && atoi(e) != 0;
@@ -1630,7 +1724,11 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (f16) {
     qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
     NWK_LAUNCH_CHECK();
-    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
+    if (l2x) {
+      qnorm_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, &sc->qn2max);
+      NWK_LAUNCH_CHECK();
+    }
+    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, pl.pitch, metric, direct ? 1 : 0, sc, qh);
     NWK_LAUNCH_CHECK();
   }
   {
@@ -1644,28 +1742,28 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
       so.ns = pl.ns; so.ns_pad = pl.ns_pad;
       so.rows = srows; so.alpha = salpha; so.beta = sbeta;
     }
-    if (direct && metric != NWK_METRIC_COSINE) {
+    if (direct && metric == NWK_METRIC_DOT) {
       // the one extra pass the direct keys cost: the global scale needs max |b_ij| before any row is converted
       qmax_kernel<<<sms * 8, 256, 0, s>>>(base, nb * d, &sc->babsmax);
       NWK_LAUNCH_CHECK();
     }
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0);
-    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, 0);
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, 0, pl.dh);
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[1], s);
 
   CUtensorMap tm_q, tm_b;
   if (f16) {
-    NWK_TRY(make_tmap(&tm_q, qh, nq, pl.dh, true, TQ));
-    NWK_TRY(make_tmap(&tm_b, bh, nb, pl.dh, true, TB));
+    NWK_TRY(make_tmap(&tm_q, qh, nq, pl.kcols, true, TQ, pl.pitch));
+    NWK_TRY(make_tmap(&tm_b, bh, nb, pl.kcols, true, TB, pl.pitch));
   } else {
     NWK_TRY(make_tmap(&tm_q, query, nq, d, false, TQ));
     NWK_TRY(make_tmap(&tm_b, base, nb, d, false, TB));
   }
 
   TcParams p{};
-  p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
+  p.nKB = pl.nKB; p.kLast = pl.kLast; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
   p.sc = sc; p.metric = metric;
@@ -1687,7 +1785,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     NWK_LAUNCH_CHECK();
     // the sample pass scans the compact matrix of sampled rows with their own alpha / beta
     CUtensorMap tm_s;
-    if (f16) NWK_TRY(make_tmap(&tm_s, srows, pl.ns, pl.dh, true, TB));
+    if (f16) NWK_TRY(make_tmap(&tm_s, srows, pl.ns, pl.kcols, true, TB, pl.pitch));
     else NWK_TRY(make_tmap(&tm_s, srows, pl.ns, d, false, TB));
     TcParams ps = p;
     ps.alpha = salpha; ps.beta = sbeta; ps.nT = pl.nS;
@@ -1715,6 +1813,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   // plus the fp32 accumulation inside the tensor core, budgeted at 4 ulp per MMA step.
   const double steps = (double)d / (f16 ? 16.0 : 8.0) + 2.0;
   f.c_rel = (float)((f16 ? 1.0 / 1024.0 : 1.0 / 512.0) * 1.001 + steps / 4194304.0);
+  f.c_acc = (float)((steps + 1.0) / 4194304.0);
   f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   if (bound) {
     tau_bound_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(f, bound, bound_stride, tau, bflag);
@@ -1730,7 +1829,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     pp.nChunks = (pl.nT + pp.G - 1) / pp.G;
     pp.nUnits = pp.nChunks * pp.nQT;
     CUtensorMap tm_bh;
-    NWK_TRY(make_tmap(&tm_bh, bh, nb, pl.dh, true, TB / 2));
+    NWK_TRY(make_tmap(&tm_bh, bh, nb, pl.kcols, true, TB / 2, pl.pitch));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2u * (unsigned)(pp.nUnits < clusters ? pp.nUnits : clusters));
     cfg.blockDim = dim3(TC_THREADS);
@@ -1793,6 +1892,16 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   NWK_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
   NWK_CUDA(cudaStreamSynchronize(s));
   if (h.err != 0) return fail(NWK_ERR_INTERNAL, "tcgen05 pipeline watchdog expired (role code %d)", h.err);
+  if (h.overflow) {
+    // direct squared-L2 keys: some |b|^2 does not fit the scale taken from the queries (base rows
+    // more than ~11 x longer than the longest query): repeat the call with alpha / beta keys
+    if (profile) for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+    const long long first_pass = g_launches.load() - launches0;
+    const int rc = tc_knn(base, nb, query, nq, d, k, metric, id_offset, out_dist, out_idx, ws, ws_bytes,
+                          flags | NWK_FLAG_ALPHA_BETA, stats, s, bound, bound_stride);
+    if (rc == NWK_OK && stats) stats->gpu_launches += (int)first_pass;
+    return rc;
+  }
   float err_ratio;
   memcpy(&err_ratio, &h.err_ratio, 4);
   if (err_ratio > 1.0f)
@@ -1865,14 +1974,14 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_CUDA(cudaMalloc(&qh, (size_t)nq * pl.dh * 2));
     qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
     NWK_LAUNCH_CHECK();
-    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, sc, qh);
+    qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, pl.dh, NWK_METRIC_DOT, 0, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0);
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0);
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);
@@ -1880,7 +1989,7 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
   int h = 0;
   if (rc == NWK_OK) {
     TcParams p{};
-    p.nKB = pl.nKB; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
+    p.nKB = pl.nKB; p.kLast = pl.kLast; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
     p.dump = out; p.dump_qt = (int)(q0 / TQ); p.dump_t = (int)(b0 / TB); p.err = &sc->err;
     rc = f16 ? launch_tc<true>(MODE_DUMP, 1, tm_q, tm_b, p, s) : launch_tc<false>(MODE_DUMP, 1, tm_q, tm_b, p, s);
     if (rc == NWK_OK) {

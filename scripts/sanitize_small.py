@@ -23,4 +23,16 @@ m_d, m_i = knn.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] 
 assert torch.equal(m_d, d3)
 assert fmt.validate_pairs(base, q, m_i, m_d) == 0
 o_d, o_i = knn.knn_host(base.cpu().numpy(), q.cpu().numpy(), 100, metric="cosine", slab_rows=6000)
+# CTA-pair filter (d >= 512) with both key forms, resident query tile with alpha / beta keys, running search
+b768 = synth.device_vectors(6000, 768, 1234, device=dev)
+q768 = synth.device_vectors(300, 768, 5678, device=dev)
+for metric in ("sqeuclidean", "cosine"):
+    knn.knn(b768, q768, 100, metric=metric)
+    print("pair", metric, knn.last_stats["path"], knn.last_stats["n_fallback_queries"])
+st = knn.RunningTopK(300, 100, dev)
+for lo in range(0, 20000, 5000):
+    st.search(base[lo:lo + 5000], q, metric="sqeuclidean", id_offset=lo)
+r_d, r_i = st.result()
+assert torch.equal(r_d, d3)
+st.close()
 print("ok")

@@ -123,12 +123,10 @@ def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
 ])
 def test_tc_filter_variants(cuda_device, monkeypatch, pair, ares, direct, nq, nb, d, k, metric):
     """The CTA-pair (cta_group::2) and single-CTA filter kernels, with per-column alpha / beta keys
-    or direct keys (one global base scale; dot and cosine only), must all reproduce the oracle,
+    or direct keys (one global base scale; squared L2 with |b|^2 in extra K columns), must all reproduce the oracle,
     whatever the planner would have picked for the shape (NWK_PAIR / NWK_DIRECT are the library's
     experiment switches)."""
     from neighborhoodwatch_b200 import knn
-    if direct == "1" and metric == "sqeuclidean":
-        pytest.skip("direct keys are not built for squared L2")
     monkeypatch.setenv("NWK_PAIR", pair)
     monkeypatch.setenv("NWK_DIRECT", direct)
     monkeypatch.setenv("NWK_ARES", ares)
@@ -174,7 +172,7 @@ def test_tc_gaussian_unnormalised(cuda_device):
 
 
 @pytest.mark.parametrize("direct", ["0", "1"], ids=["alpha-beta-keys", "direct-keys"])
-@pytest.mark.parametrize("metric", ["dot", "cosine"])
+@pytest.mark.parametrize("metric", ["dot", "cosine", "sqeuclidean"])
 def test_tc_signed_rows_with_unrankable_entries(cuda_device, monkeypatch, metric, direct):
     """Signed vectors of very different lengths, a ragged last tile, zero vectors (no cosine) and rows
     with inf / nan entries: such rows must never be returned, by either key form."""
@@ -193,12 +191,29 @@ def test_tc_signed_rows_with_unrankable_entries(cuda_device, monkeypatch, metric
     st = dict(knn.last_stats)
     assert st["path"] == 1 and st["max_err_ratio"] <= 1.0, st
     got_i = got_i.cpu().numpy()
-    skip = bad[1:3] if metric == "dot" else bad          # a zero vector has a dot product, but no cosine
+    skip = bad if metric == "cosine" else bad[1:3]       # a zero vector has a dot product and a distance, but no cosine
     assert not np.isin(got_i, skip).any()
     keep = np.setdiff1d(np.arange(nb), skip)
     t_d, t_i = ko.knn_f64(base[keep], q, k, metric, return_f64=True)
     res = ko.compare_knn(got_d.cpu().numpy(), got_i, base, q, metric, t_d, keep[t_i], rtol=1e-5, atol=1e-6, tie_rtol=1e-6)
     print(metric, direct, st, res)
+
+
+@pytest.mark.parametrize("ratio,expect_direct", [(4.0, True), (40.0, False)])
+def test_l2_direct_keys_scale_overflow(cuda_device, ratio, expect_direct):
+    """Direct squared-L2 keys take their scale from the query norms; base rows more than ~11 x longer
+    than the longest query do not fit it and the call must repeat itself with alpha / beta keys."""
+    from neighborhoodwatch_b200 import knn
+    base = synth.vectors(30000, 128, 1234) * np.float32(ratio)
+    base[::7] *= np.float32(0.25)                       # mixed lengths
+    q = synth.vectors(200, 128, 5678)
+    got_d, got_i = knn.knn(_dev(base, cuda_device), _dev(q, cuda_device), 100, metric="sqeuclidean", profile=True)
+    st = dict(knn.last_stats)
+    assert st["path"] == 1 and st["max_err_ratio"] <= 1.0, st
+    # the repeated call launches the whole pipeline twice
+    assert (st["gpu_launches"] <= 14) == expect_direct, st
+    _check(got_d, got_i, base, q, 100, "sqeuclidean")
+    print(ratio, st)
 
 
 def test_tc_duplicates_fall_back_and_stay_exact(cuda_device):
