@@ -57,6 +57,7 @@ constexpr int STAGES = 4;
 constexpr int PAIR_STAGES = 6;                  // operand ring of the CTA-pair filter kernel (32 KB per stage and CTA)
 constexpr int ACC_STAGES = 2;
 constexpr int TC_THREADS = 384;                // 4 control warps + 2 epilogue warpgroups
+constexpr int TC_THREADS_WIDE = 640;           // ... + 4 epilogue warpgroups (direct keys on a single CTA, see epi_wg())
 constexpr int EPI_WG_MAX = 2;
 constexpr int STAGE_A_BYTES = TQ * 128;        // 16 KB: 128 rows x one 128-byte swizzle span
 constexpr int STAGE_B_BYTES = TB * 128;        // 32 KB
@@ -525,8 +526,17 @@ struct Sched {
 // single-CTA kernel is bound by exactly that traffic (measured with the epilogue switched off:
 // 96 KB per 128 x 256 x 128 tile arrive in 1640 clk, the MMAs need 1024).  Short rows only: the
 // tile's whole K extent (p.nKB x 16 KB, at most 96 KB) must fit beside a ring of base stages.
+// Epilogue warpgroups of a variant.  Direct keys on a single CTA are the short-row kernels, whose
+// epilogue is bound by the latency of its slow path (1.9 hit groups per warp and tile at d = 128,
+// ~600 clk each, issue slots 34 % busy with two warps per scheduler): four warpgroups = four warps
+// per scheduler, each over a quarter of the columns, within 96 registers per thread.
+template <int MODE, bool CTA2, bool DIRECT>
+__host__ __device__ constexpr int epi_wg() {
+  return MODE == MODE_DUMP ? 1 : ((MODE == MODE_FILTER && DIRECT && !CTA2) ? 4 : 2);
+}
+
 template <int MODE, bool F16, bool CTA2 = false, bool DIRECT = false, bool ARES = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(128 + 128 * epi_wg<MODE, CTA2, DIRECT>(), 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
           const TcParams p) {
   static_assert(!CTA2 || (MODE == MODE_FILTER && F16), "CTA pairs are built for the fp16 filter pass");
@@ -542,7 +552,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
   const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;
   // the filter pass splits the 256 accumulator columns over two epilogue warpgroups; the sample
   // pass keeps one (its per-query list lives in one thread's registers)
-  constexpr int EPI_WG = (MODE == MODE_DUMP) ? 1 : 2;
+  constexpr int EPI_WG = epi_wg<MODE, CTA2, DIRECT>();
+  // per-thread record staging: EPI_WG_MAX warpgroups x APPEND_SLOTS in s_app; the four direct-key
+  // warpgroups have no alpha / beta, so theirs starts at s_ab and also takes the unused mask block
+  constexpr int ASLOTS = EPI_WG > EPI_WG_MAX ? (AB_BYTES + APPEND_BYTES + MASK_BYTES) / (TQ * EPI_WG * 8) : APPEND_SLOTS;
+  static_assert(ASLOTS >= 4, "record staging");
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   // (offset arithmetic on the __shared__ pointer keeps its address space: LDS/STS, not generic LD/ST)
@@ -900,8 +914,32 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // `hits`).  General keys: alpha_j + beta_j * acc (one FFMA per element, alpha / beta read as
       // broadcast LDS.128 -- those reads are what bounds this variant).  Direct keys: the
       // accumulator itself against thr = tau / kscale, no shared-memory traffic at all. ----
-      uint32_t va[32], vb[32];
       uint32_t hits = 0;
+      if (EPI_WG > EPI_WG_MAX) {
+        // four warpgroups (direct keys): 64 columns per warp as four 16-column loads, two in flight,
+        // so the whole epilogue fits 96 registers per thread
+        if (p.dbg != 2) {
+          uint32_t wa[16], wb[16];
+          ptx::tmem_ld_32x16(taddr + c0 * 32, wa);
+#pragma unroll
+          for (int h = 0; h < CPW * 2; ++h) {
+            ptx::tmem_wait_ld();
+            uint32_t(&cur)[16] = (h & 1) ? wb : wa;
+            uint32_t(&nxt)[16] = (h & 1) ? wa : wb;
+            if (h + 1 < CPW * 2) ptx::tmem_ld_32x16(taddr + c0 * 32 + (h + 1) * 16, nxt);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float m = fmaxf(__uint_as_float(cur[8 * g]), __uint_as_float(cur[8 * g + 1]));
+#pragma unroll
+              for (int j = 2; j < 8; j += 2)
+                m = fmaxf(m, fmaxf(__uint_as_float(cur[8 * g + j]), __uint_as_float(cur[8 * g + j + 1])));
+              if (m > thr) hits |= 1u << (h * 2 + g);     // bit = group of 8 columns, counted from this warp's first column
+            }
+          }
+          ptx::tmem_wait_ld();
+        }
+      } else {
+      uint32_t va[32], vb[32];
       if (p.dbg != 2) {
       ptx::tmem_ld_32x32(taddr + c0 * 32, va);
 #pragma unroll
@@ -942,6 +980,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       }
       ptx::tmem_wait_ld();
       }
+      }
 
       // ---- slow path (rare): groups where some lane of the warp has a hit.  One rolled loop:
       // re-read the group's 8 columns from TMEM, recompute the keys (bit-identical to the fast
@@ -953,7 +992,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // trip with their loads and compare chains interleaved: +9 %.) ----
       if (MODE == MODE_FILTER) {
         uint32_t um = __reduce_or_sync(0xffffffffu, hits);
-        unsigned long long* const slots = s_app + etid;
+        unsigned long long* const slots = (EPI_WG > EPI_WG_MAX ? reinterpret_cast<unsigned long long*>(s_ab) : s_app) + etid;
         while (um) {                                   // warp-uniform
           const int b = __ffs(um) - 1;
           um &= um - 1;
@@ -989,12 +1028,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
               slots[nst * (TQ * EPI_WG)] = (static_cast<unsigned long long>(f2ord(kj)) << 32) |
                                            static_cast<unsigned long long>(row);
             nst += take ? 1 : 0;
-            if (__any_sync(0xffffffffu, nst == APPEND_SLOTS)) {
-              if (nst == APPEND_SLOTS) {
+            if (__any_sync(0xffffffffu, nst == ASLOTS)) {
+              if (nst == ASLOTS) {
                 // one global atomic reserves log space for the lane's batch of staged records
-                const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)APPEND_SLOTS);
+                const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)ASLOTS);
 #pragma unroll
-                for (int i = 0; i < APPEND_SLOTS; ++i)
+                for (int i = 0; i < ASLOTS; ++i)
                   if (base + i < LOG_CAP) p.log[q * LOG_CAP + base + i] = slots[i * (TQ * EPI_WG)];
                 nst = 0;
               }
@@ -1018,7 +1057,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       if (MODE == MODE_FILTER && last && nst > 0) {
         const unsigned int base = atomicAdd(p.cnt + q, (unsigned int)nst);
         for (int j = 0; j < nst; ++j)
-          if (base + j < LOG_CAP) p.log[q * LOG_CAP + base + j] = s_app[j * (TQ * EPI_WG) + etid];
+          if (base + j < LOG_CAP)
+            p.log[q * LOG_CAP + base + j] =
+                (EPI_WG > EPI_WG_MAX ? reinterpret_cast<unsigned long long*>(s_ab) : s_app)[j * (TQ * EPI_WG) + etid];
         nst = 0;
       }
     }
@@ -1655,7 +1696,7 @@ static int launch_tc(int mode, int grid, const CUtensorMap& tq, const CUtensorMa
                      cudaStream_t s) {
   if (mode == MODE_SAMPLE) tc_kernel<MODE_SAMPLE, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
   else if (mode == MODE_FILTER) tc_kernel<MODE_FILTER, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
-  else tc_kernel<MODE_DUMP, F16><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tq, tb, p);
+  else tc_kernel<MODE_DUMP, F16><<<grid, 128 + 128 * epi_wg<MODE_DUMP, false, false>(), TC_SMEM_BYTES, s>>>(tq, tb, p);
   NWK_LAUNCH_CHECK();
   return NWK_OK;
 }
@@ -1845,8 +1886,8 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     count_launch();
   } else if (direct || ares) {
     int grid = pl.nUnits < sms ? pl.nUnits : sms;
-    if (direct && ares) tc_kernel<MODE_FILTER, true, false, true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    else if (direct) tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    if (direct && ares) tc_kernel<MODE_FILTER, true, false, true, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
+    else if (direct) tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
     else tc_kernel<MODE_FILTER, true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
     NWK_LAUNCH_CHECK();
   } else {
