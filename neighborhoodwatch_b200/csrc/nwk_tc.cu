@@ -989,7 +989,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // cost more here than the arithmetic (measured: 30 % of the loop's stall samples).
       // (Measured alternatives at d = 128: doing this work inside the fast path, while the values
       // are still in registers, behind one vote per group: +18 % filter time; four groups per
-      // trip with their loads and compare chains interleaved: +9 %.) ----
+      // trip with their loads and compare chains interleaved: +9 %; releasing the accumulator
+      // stage first and working on hit groups stashed in registers afterwards: +2..4 % -- the
+      // warps' total work per tile, not the slowest warp, is what the tile waits for.) ----
       if (MODE == MODE_FILTER) {
         uint32_t um = __reduce_or_sync(0xffffffffu, hits);
         unsigned long long* const slots = (EPI_WG > EPI_WG_MAX ? reinterpret_cast<unsigned long long*>(s_ab) : s_app) + etid;
