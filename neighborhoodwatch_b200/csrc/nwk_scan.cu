@@ -342,6 +342,93 @@ int exact_scan(const float* base, long long nb, const float* query, int d, int k
 // ---------------------------------------------------------------------------------------
 // merge driver
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// rank merge: P lists of k_in records per query, P * k_in <= RANK_MERGE_MAX.  One warp per query
+// with the lists in shared memory.  Lists that are non-decreasing in distance (what knn() and
+// the running state produce) are merged by ranking: an element's slot in the output is the number
+// of elements ordered before it, found by one binary search per list plus a scan over the (rare)
+// equal distances; +inf entries are padding and stay out.  A query whose lists are not sorted is
+// ranked by counting over all pairs instead.  Order: (distance, index, list, position) -- the
+// first two are the documented order, the last two only separate exact duplicates.  NaN sorts
+// as +inf.  (The segmented bitonic sort this replaces for small merges took 0.9 ms for 10 000
+// queries x 8 lists x 100; the all-gather + merge of an 8-GPU step 1.37 ms.)
+// ---------------------------------------------------------------------------------------
+constexpr int RANK_MERGE_MAX = 2048;
+constexpr int RANK_MERGE_THREADS = 128;
+
+__global__ void __launch_bounds__(RANK_MERGE_THREADS)
+merge_rank_kernel(const float* __restrict__ dist, const long long* __restrict__ idx, int P, long long nq, int k_in,
+                  int k_out, float* __restrict__ out_dist, long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) unsigned char rm_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = P * k_in;
+  long long* s_id = reinterpret_cast<long long*>(rm_smem) + (size_t)warp * n;
+  float* s_d = reinterpret_cast<float*>(rm_smem + (size_t)(RANK_MERGE_THREADS / 32) * n * 8) + (size_t)warp * n;
+  const long long q = (long long)blockIdx.x * (RANK_MERGE_THREADS / 32) + warp;
+  if (q >= nq) return;
+  const float INF = __int_as_float(0x7f800000);
+  bool sorted = true;
+  for (int e = lane; e < n; e += 32) {
+    const int b = e / k_in, j = e - b * k_in;
+    const size_t g = ((size_t)b * nq + q) * k_in + j;
+    float d = dist[g];
+    if (!(d == d)) d = INF;
+    s_d[e] = d;
+    s_id[e] = idx[g];
+  }
+  for (int j = lane; j < k_out; j += 32) { out_dist[q * k_out + j] = INF; out_idx[q * k_out + j] = -1; }
+  __syncwarp();
+  for (int e = lane; e < n; e += 32)
+    if ((e % k_in) != 0 && s_d[e - 1] > s_d[e]) sorted = false;
+  sorted = __all_sync(0xffffffffu, sorted);
+  for (int e = lane; e < n; e += 32) {
+    const float d = s_d[e];
+    if (!(d < INF)) continue;                       // padding
+    const long long id = s_id[e];
+    const int a = e / k_in;
+    int rank = 0;
+    if (sorted) {
+      for (int b = 0; b < P; ++b) {
+        const float* l = s_d + b * k_in;
+        int lo = 0, hi = k_in;                      // first position with l[pos] >= d
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (l[mid] < d) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+        for (int pos = lo; pos < k_in && l[pos] == d; ++pos) {
+          const int f = b * k_in + pos;
+          const long long fid = s_id[f];
+          if (fid < id || (fid == id && f < e)) ++rank;
+        }
+      }
+    } else {
+      for (int f = 0; f < n; ++f) {
+        const float fd = s_d[f];
+        const long long fid = s_id[f];
+        if (fd < d || (fd == d && (fid < id || (fid == id && f < e)))) ++rank;
+      }
+    }
+    (void)a;
+    if (rank < k_out) { out_dist[q * k_out + rank] = d; out_idx[q * k_out + rank] = id; }
+  }
+}
+
+static int merge_rank(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
+                      float* out_dist, long long* out_idx, cudaStream_t s) {
+  const int n = P * k_in;
+  const int smem = (RANK_MERGE_THREADS / 32) * n * 12;
+  static int optin = 48 * 1024;
+  if (smem > optin) {
+    NWK_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    optin = smem;
+  }
+  const long long blocks = (nq + RANK_MERGE_THREADS / 32 - 1) / (RANK_MERGE_THREADS / 32);
+  merge_rank_kernel<<<(unsigned)blocks, RANK_MERGE_THREADS, smem, s>>>(dist, idx, P, nq, k_in, k_out, out_dist, out_idx);
+  NWK_LAUNCH_CHECK();
+  return NWK_OK;
+}
+
 size_t merge_workspace_bytes(int P, long long nq, int k_in, int k_out) {
   long long n = (long long)P * k_in;
   long long nseg = (n + SEG - 1) / SEG;
@@ -354,6 +441,8 @@ int merge_topk(int P, const float* dist, const long long* idx, long long nq, int
   if (nq == 0) return NWK_OK;
   if (ws_bytes < merge_workspace_bytes(P, nq, k_in, k_out))
     return fail(NWK_ERR_WORKSPACE, "merge workspace too small");
+  if ((long long)P * k_in <= RANK_MERGE_MAX && nq < (1ll << 31) * (RANK_MERGE_THREADS / 32))
+    return merge_rank(P, dist, idx, nq, k_in, k_out, out_dist, out_idx, s);
   long long n = (long long)P * k_in;
   long long nseg = (n + SEG - 1) / SEG;
   Arena ar(ws, ws_bytes);

@@ -263,6 +263,24 @@ def test_merge_parity(cuda_device):
     out_d, out_i = knn.merge_topk(torch.from_numpy(d).to(cuda_device), torch.from_numpy(i).to(cuda_device), 10)
     for r in range(3):
         assert list(out_i[r].cpu().numpy()) == sorted(i[:, r, :].ravel())[:10]
+    # lists that are not sorted (the small-merge kernel ranks them by counting instead of searching)
+    d = rng.random((5, 20, 50)).astype(np.float32)
+    i = rng.permutation(5 * 20 * 50).astype(np.int64).reshape(5, 20, 50)
+    out_d, out_i = knn.merge_topk(torch.from_numpy(d).to(cuda_device), torch.from_numpy(i).to(cuda_device), 60)
+    ref_d, ref_i = mo.merge_by_distance_then_index([(d[p], i[p]) for p in range(5)], 60)
+    np.testing.assert_array_equal(out_d.cpu().numpy(), ref_d)
+    np.testing.assert_array_equal(out_i.cpu().numpy(), ref_i)
+    # padded lists (+inf / -1, what a bounded running search emits): fewer finite entries than k_out
+    d = np.sort(rng.random((3, 8, 40)).astype(np.float32), axis=2)
+    i = rng.permutation(3 * 8 * 40).astype(np.int64).reshape(3, 8, 40)
+    d[:, :, 10:] = np.inf
+    i[:, :, 10:] = -1
+    out_d, out_i = knn.merge_topk(torch.from_numpy(d).to(cuda_device), torch.from_numpy(i).to(cuda_device), 40)
+    out_d, out_i = out_d.cpu().numpy(), out_i.cpu().numpy()
+    ref_d, ref_i = mo.merge_by_distance_then_index([(d[p, :, :10], i[p, :, :10]) for p in range(3)], 30)
+    np.testing.assert_array_equal(out_d[:, :30], ref_d)
+    np.testing.assert_array_equal(out_i[:, :30], ref_i)
+    assert np.all(np.isinf(out_d[:, 30:])) and np.all(out_i[:, 30:] == -1)
 
 
 def test_running_topk_equals_one_shot(cuda_device):
