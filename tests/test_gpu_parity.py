@@ -98,6 +98,8 @@ def test_tc_operand_rounding_probe(cuda_device):
     (5, 150, 64, 100),           # tiny base: everything is logged, no sampling
     (129, 2049, 768, 10),        # one row past a tile boundary on both sides
     (64, 40000, 128, 256),       # k at the tensor-core path's limit
+    (50, 3000, 4, 10),           # the shortest rows the tensor-core path takes: one K-block, one MMA step
+    (70, 9000, 12, 20),          # (squared L2's extra columns share that block)
 ])
 def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     from neighborhoodwatch_b200 import knn
