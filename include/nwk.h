@@ -164,6 +164,25 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
                      float* out_dist_host, int64_t* out_idx_host, uint32_t flags,
                      nwk_knn_stats* stats);
 
+/* Document-level ColBERT MaxSim (the reference's colbert_knn.py:62-126 stops at a
+ * token-level kNN over the flattened token embeddings, which nwk_knn_f32 with NWK_METRIC_DOT covers):
+ *
+ *   score(Q, D) = sum over Q's tokens t of  max over D's tokens j of  q_t . d_j,   top-k documents per query.
+ *
+ *   query_tokens [nq, tq, d] fp32 device (tq a power of two <= 128; pad shorter queries with zero tokens,
+ *                 which add 0 to every score), doc_tokens [nd, td, d] fp32 device (td <= 256),
+ *   doc_len      [nd] int32 device or NULL: valid tokens of each document (the rest is padding and ignored),
+ *   out_score    [nq, k] fp32 descending, out_idx [nq, k] int64 = document number + id_offset
+ *                (ties by document number); k <= min(256, nd); d % 4 == 0.
+ * Approximate scores come from a tcgen05 GEMM with the max / sum fused into its TMEM epilogue; the
+ * 4k best documents per query are re-scored exactly in fp64 and the result is certified against a
+ * proven error bound (uncertified queries are re-scored against all documents), like nwk_knn_f32.
+ * stats->path = 3.  Synchronises the stream. */
+size_t nwk_maxsim_workspace_bytes(int64_t nq, int32_t tq, int64_t nd, int32_t td, int32_t d, int32_t k);
+int nwk_maxsim_f32(const float* query_tokens, int64_t nq, int32_t tq, const float* doc_tokens, int64_t nd, int32_t td,
+                   const int32_t* doc_len, int32_t d, int32_t k, int64_t id_offset, float* out_score, int64_t* out_idx,
+                   void* workspace, size_t ws_bytes, nwk_knn_stats* stats, void* stream);
+
 /* Deterministic synthetic vectors (the fixture style of tests/test_02_cu_knn.py:21-28:
  * uniform[0,1) components, rows L2-normalised), counter-based so any slab of a large base
  * can be regenerated: element (row, col) depends only on (seed, row, col, d).  The numpy

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "nwk_last_error", "nwk_abi_version", "nwk_launch_count", "nwk_knn_workspace_bytes", "nwk_knn_f32",
     "nwk_merge_workspace_bytes", "nwk_merge_topk", "nwk_topk_state_create", "nwk_topk_state_update",
     "nwk_topk_state_search", "nwk_topk_state_finalize", "nwk_topk_state_destroy", "nwk_knn_host_f32", "nwk_synth_fill",
-    "nwk_debug_tc_tile", "nwk_validate_pairs",
+    "nwk_debug_tc_tile", "nwk_validate_pairs", "nwk_maxsim_workspace_bytes", "nwk_maxsim_f32",
 )
 
 
@@ -85,6 +85,11 @@ def load() -> ctypes.CDLL:
     lib.nwk_topk_state_create.argtypes = [c_int64, c_int32, POINTER(c_void_p)]
     lib.nwk_topk_state_update.restype = c_int32
     lib.nwk_topk_state_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nwk_maxsim_workspace_bytes.restype = c_size_t
+    lib.nwk_maxsim_workspace_bytes.argtypes = [c_int64, c_int32, c_int64, c_int32, c_int32, c_int32]
+    lib.nwk_maxsim_f32.restype = c_int32
+    lib.nwk_maxsim_f32.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32,
+                                   c_int64, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(KnnStats), c_void_p]
     lib.nwk_topk_state_search.restype = c_int32
     lib.nwk_topk_state_search.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int64, c_void_p,
                                           c_size_t, c_uint32, POINTER(KnnStats), c_void_p]

@@ -4,7 +4,9 @@ Only the kNN entry point of ``ck`` is on the hot path (SURVEY.md section 8, row 
 token-embedding dataset builder needs network + model weights and is out of scope.  As in
 the reference this is *flattened token-level* kNN: every query-token vector is a query and
 every document-token vector a base row, with the torch engine's ``1 - q.b`` distance
-(cu_knn.py:256) -- not a document-level MaxSim.
+(cu_knn.py:256) -- not a document-level MaxSim.  ``maxsim_topk`` below adds that score as an extra
+metric: the reference never computes it, so its parity is pinned by
+``oracle/maxsim_oracle.py`` only.
 """
 from __future__ import annotations
 
@@ -47,3 +49,14 @@ def process_knn_computation(data_dir,
         f"Cannot generate k of {k} with only {len(base_table)} rows and batch_size of {batch_size}."
 
     process_batches(data_dir, base_table, query_table, batch_count, batch_size, k, split, engine=engine)
+
+
+def maxsim_topk(query_tokens, doc_tokens, k=100, doc_len=None, id_offset=0):
+    """Top-k documents per query by ColBERT MaxSim, ``score(Q, D) = sum_t max_j q_t . d_j``.
+
+    ``query_tokens`` [n_queries, query_maxlen, d] and ``doc_tokens`` [n_docs, doc_maxlen, d] are the
+    per-token embeddings the reference flattens into its ``token_embedding_*`` files
+    (colbert_knn.py:62-66,229); ``doc_len`` gives the valid tokens of ragged documents.
+    """
+    from . import knn as _knn
+    return _knn.maxsim_topk(query_tokens, doc_tokens, k, doc_len=doc_len, id_offset=id_offset)

@@ -25,6 +25,10 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
                   long long q0, float* out, int use_f16, cudaStream_t s);
 int synth_fill(float* out, long long rows, int d, unsigned long long seed, long long row0, int normalize,
                cudaStream_t s);
+size_t maxsim_workspace_bytes(long long nq, int Tq, long long nd, int Td, int d, int k);
+int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long long nd, int Td, const int* doc_len, int d,
+                int k, long long id_offset, float* out_score, long long* out_idx, void* ws, size_t ws_bytes,
+                nwk_knn_stats* stats, cudaStream_t s);
 
 int validate_pairs(const float* base, long long nb, const float* query, long long nq, int d, const long long* idx,
                    const float* dist, int k, double rtol, double atol, long long* out_host, cudaStream_t s);
@@ -397,6 +401,22 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
   if (st) nwk_topk_state_destroy(st);
   if (stats && rc == NWK_OK) *stats = total;
   return rc;
+}
+
+size_t nwk_maxsim_workspace_bytes(int64_t nq, int32_t tq, int64_t nd, int32_t td, int32_t d, int32_t k) {
+  if (nq <= 0 || nd <= 0 || tq <= 0 || td <= 0 || d <= 0 || k <= 0) return 256;
+  return maxsim_workspace_bytes(nq, tq, nd, td, d, k);
+}
+
+int nwk_maxsim_f32(const float* query_tokens, int64_t nq, int32_t tq, const float* doc_tokens, int64_t nd, int32_t td,
+                   const int32_t* doc_len, int32_t d, int32_t k, int64_t id_offset, float* out_score, int64_t* out_idx,
+                   void* workspace, size_t ws_bytes, nwk_knn_stats* stats, void* stream) {
+  if (!query_tokens || !doc_tokens || !out_score || !out_idx || !workspace) return fail(NWK_ERR_ARG, "null pointer argument");
+  NWK_TRY(device_check());
+  if (((reinterpret_cast<uintptr_t>(query_tokens) | reinterpret_cast<uintptr_t>(doc_tokens)) & 15u) != 0)
+    return fail(NWK_ERR_ARG, "maxsim: token arrays must be 16-byte aligned");
+  return maxsim_topk(query_tokens, nq, tq, doc_tokens, nd, td, doc_len, d, k, id_offset, out_score, (long long*)out_idx,
+                     workspace, ws_bytes, stats, static_cast<cudaStream_t>(stream));
 }
 
 int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0, int32_t normalize,

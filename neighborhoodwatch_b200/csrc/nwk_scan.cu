@@ -246,6 +246,49 @@ static int run_topk_rounds(SegArgs a, int F, double* ping_k, long long* ping_i, 
 }
 
 // ---------------------------------------------------------------------------------------
+// k smallest of F rows of n double keys (id = position + id_offset), for callers outside this
+// file (the MaxSim path): out_key fp32 / out_idx int64 at row `qsel ? qsel[f] : f`.
+// ---------------------------------------------------------------------------------------
+size_t topk_from_keys_workspace_bytes(long long n, long long F, int k) {
+  const long long nseg = (n + SEG - 1) / SEG;
+  if (F > 32768) F = 32768;
+  return nseg > 1 ? (size_t)F * nseg * k * 16 * 2 + 4096 : 256;
+}
+
+int topk_from_keys(const double* keys, long long n, long long stride, long long F, int k, const int* qsel,
+                   long long id_offset, float* out_key, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (F == 0) return NWK_OK;
+  if (ws_bytes < topk_from_keys_workspace_bytes(n, F, k)) return fail(NWK_ERR_WORKSPACE, "top-k workspace too small");
+  const long long nseg = (n + SEG - 1) / SEG;
+  const long long SLICE = 32768;                       // grid.y limit
+  const long long fc = F < SLICE ? F : SLICE;
+  Arena ar(ws, ws_bytes);
+  double* ping_k = nullptr; long long* ping_i = nullptr; double* pong_k = nullptr; long long* pong_i = nullptr;
+  if (nseg > 1) {
+    ping_k = ar.take<double>((size_t)fc * nseg * k);
+    ping_i = ar.take<long long>((size_t)fc * nseg * k);
+    pong_k = ar.take<double>((size_t)fc * nseg * k);
+    pong_i = ar.take<long long>((size_t)fc * nseg * k);
+  }
+  for (long long f0 = 0; f0 < F; f0 += SLICE) {
+    const int nf = (int)min(SLICE, F - f0);
+    SegArgs a{};
+    a.in_key = keys + f0 * stride;
+    a.n = n;
+    a.in_stride = stride;
+    a.k = k;
+    a.out_dist = out_key;
+    a.out_idx = out_idx;
+    a.id_offset = id_offset;
+    a.qsel = qsel;
+    a.f0 = (int)f0;
+    if (!qsel) { a.out_dist = out_key + f0 * k; a.out_idx = out_idx + f0 * k; }
+    NWK_TRY(run_topk_rounds<SRC_IOTA>(a, nf, ping_k, ping_i, pong_k, pong_i, s));
+  }
+  return NWK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // exact scan driver
 // ---------------------------------------------------------------------------------------
 static long long scan_chunk_queries(long long nb) {

@@ -2051,4 +2051,6 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
   return NWK_OK;
 }
 
+#include "nwk_maxsim.cuh"
+
 }  // namespace nwk

@@ -232,3 +232,45 @@ def debug_tc_tile(dataset: torch.Tensor, queries: torch.Tensor, b0: int, q0: int
                                    dataset.shape[1], b0, q0, out.data_ptr(), 1 if f16 else 0, _stream_ptr(dev))
         _native.check(rc)
     return out
+
+
+def maxsim_topk(query_tokens: torch.Tensor, doc_tokens: torch.Tensor, k: int, doc_len: Optional[torch.Tensor] = None,
+                id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Document-level ColBERT MaxSim (nwk_maxsim_f32): ``score(Q, D) = sum_t max_j q_t . d_j``.
+
+    ``query_tokens`` [nq, Tq, d] (Tq a power of two <= 128; pad with zero tokens), ``doc_tokens``
+    [nd, Td, d] (Td <= 256), ``doc_len`` optional int32 [nd] valid tokens per document.
+    Returns (scores f32 [nq, k] descending, document ids i64 [nq, k] + id_offset).
+    """
+    global last_stats
+    lib = _native.load()
+    for name, x in (("query_tokens", query_tokens), ("doc_tokens", doc_tokens)):
+        if not isinstance(x, torch.Tensor) or x.device.type != "cuda":
+            raise RuntimeError(f"{name} must be a CUDA tensor; this engine has no CPU path")
+        if x.dim() != 3:
+            raise ValueError(f"{name} must be 3-D [n, tokens, d]")
+    q = query_tokens.to(torch.float32).contiguous()
+    dd = doc_tokens.to(torch.float32).contiguous()
+    nq, tq, d = q.shape
+    nd, td, d2 = dd.shape
+    if d != d2:
+        raise ValueError(f"dimension mismatch: queries d={d}, documents d={d2}")
+    assert k <= nd, f"k={k} exceeds the {nd} documents"
+    dev = q.device
+    dl_ptr = None
+    if doc_len is not None:
+        doc_len = doc_len.to(device=dev, dtype=torch.int32).contiguous()
+        assert doc_len.shape == (nd,)
+        dl_ptr = doc_len.data_ptr()
+    with torch.cuda.device(dev):
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        ws_bytes = lib.nwk_maxsim_workspace_bytes(nq, tq, nd, td, d, k)
+        ws = _workspace(ws_bytes, dev)
+        stats = _native.KnnStats()
+        rc = lib.nwk_maxsim_f32(q.data_ptr(), nq, tq, dd.data_ptr(), nd, td, dl_ptr, d, k, int(id_offset),
+                                out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(stats),
+                                _stream_ptr(dev))
+        _native.check(rc)
+        last_stats = stats.as_dict()
+    return out_s, out_i

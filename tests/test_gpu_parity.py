@@ -495,3 +495,41 @@ def test_clustered_base_sorted_by_cluster(cuda_device):
         _check(got_d, got_i, base, q, 100, metric)
         assert st["path"] == 1 and st["max_err_ratio"] <= 1.0
         print(metric, st)
+
+
+@pytest.mark.parametrize("nq,tq,nd,td,d,k,ragged", [
+    (24, 32, 3000, 180, 128, 100, False),     # the ColBERT shape of BASELINE config 5 (query_maxlen 32, doc_maxlen 180, d 128)
+    (9, 32, 700, 180, 128, 50, True),         # ragged documents, an odd number of queries (the last query tile is mostly padding)
+    (40, 8, 500, 64, 96, 10, True),           # short queries: 16 of them per 128-row tile; d not a multiple of 64
+    (6, 64, 400, 256, 64, 20, False),         # queries of two warps' worth of tokens (summed by atomics), the longest documents
+    (5, 32, 30, 33, 128, 30, True),           # every document is a candidate
+])
+def test_maxsim_parity(cuda_device, nq, tq, nd, td, d, k, ragged):
+    """Document-level MaxSim through the C ABI against the float64 oracle (oracle/maxsim_oracle.py):
+    scores within 1e-5 relative, document ids identical except where exact scores tie within 1e-6."""
+    import torch
+    from oracle import maxsim_oracle as mso
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(7)
+    qt = rng.standard_normal((nq, tq, d)).astype(np.float32)
+    qt /= np.linalg.norm(qt, axis=2, keepdims=True)
+    dt = rng.standard_normal((nd, td, d)).astype(np.float32)
+    dt /= np.linalg.norm(dt, axis=2, keepdims=True)
+    doc_len = None
+    if ragged:
+        doc_len = rng.integers(1, td + 1, size=nd).astype(np.int32)
+        doc_len[::97] = 0                                       # empty documents never rank
+    got_s, got_i = knn.maxsim_topk(torch.from_numpy(qt).to(cuda_device), torch.from_numpy(dt).to(cuda_device), k,
+                                   doc_len=None if doc_len is None else torch.from_numpy(doc_len).to(cuda_device), id_offset=3)
+    st = dict(knn.last_stats)
+    assert st["path"] == 3 and st["max_err_ratio"] <= 1.0, st
+    got_s, got_i = got_s.cpu().numpy(), got_i.cpu().numpy()
+    full = mso.maxsim_scores_f64(qt, dt, doc_len)
+    t_s, t_i = mso.maxsim_topk_f64(qt, dt, k, doc_len)
+    finite = np.isfinite(t_s)
+    np.testing.assert_allclose(got_s[finite], t_s[finite], rtol=1e-5, atol=1e-6)
+    assert np.all(np.diff(got_s, axis=1)[finite[:, 1:]] <= 0)
+    mism = np.argwhere((got_i - 3 != t_i) & finite)
+    for r, c in mism:                                           # only exact ties may swap
+        assert abs(full[r, got_i[r, c] - 3] - t_s[r, c]) <= 1e-6 * max(1.0, abs(t_s[r, c])), (r, c)
+    print((nq, tq, nd, td, d, k, ragged), st, len(mism))
