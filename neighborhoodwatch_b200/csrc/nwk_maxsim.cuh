@@ -207,6 +207,17 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, ACC_STAGES * TB); }
 }
 
+// E_q: proven bound on |approximate - exact| score of one query = sum over its tokens of the direct-dot
+// bound of key_error_bound() (operand rounding + accumulation, quantisation of tiny elements on both
+// sides), plus the fp32 roundings of the epilogue's sum and of the stored key.  sum_norm = sum_t |q_t|.
+__device__ __forceinline__ double ms_error_bound(const Scalars* sc, float c_rel, int Tq, int d, double sum_norm) {
+  int sq, sb;
+  direct_exps(NWK_METRIC_DOT, sc, sq, sb);
+  const double dmax = sqrt((double)__uint_as_float(sc->bn2max));
+  return ((double)c_rel * dmax + ldexp(1.0, -25 - sb) * sqrt((double)d) + 4e-6 * dmax) * sum_norm +
+         Tq * ldexp(1.0, -25 - sq) * sqrt((double)d) * dmax + 1e-30;
+}
+
 // exact fp64 MaxSim of (query, document) pairs: grid (pairs per query, queries); lane = query token,
 // warp = document tokens j = warp, warp + 8, ...; the query sits transposed in shared memory.
 struct MsExact {
@@ -216,6 +227,9 @@ struct MsExact {
   const long long* cand;      // [.][nc] document ids per (selected) query, or null = documents 0..nc-1
   long long nc;
   double* out;                // [.][nc]  -(exact score)
+  // candidates only: a document whose approximate key lies more than 2 E_q above the k-th best cannot be
+  // among the true top k and is not scored (its slot gets +inf)
+  const float* cand_key; int k; const Scalars* sc; float c_rel;
 };
 
 __global__ void __launch_bounds__(256)
@@ -240,6 +254,29 @@ ms_exact_kernel(const MsExact a) {
   }
   const int valid = a.doc_len ? max(0, min(a.doc_len[doc], a.Td)) : a.Td;
   __syncthreads();
+  if (a.cand_key) {
+    // sum_t |q_t| from the transposed copy (warp w: tokens w, w + 8, ...), then the band test
+    double sn = 0.0;
+    for (int t = warp; t < a.Tq; t += 8) {
+      float n2 = 0.f;
+      for (int c = lane; c < a.d; c += 32) { const float v = s_qT[c * a.Tq + t]; n2 = fmaf(v, v, n2); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      sn += sqrt((double)n2);
+    }
+    if (lane == 0) s_max[warp] = sn;
+    __syncthreads();
+    double sum_norm = 0.0;
+    for (int w = 0; w < 8; ++w) sum_norm += s_max[w];
+    const double E = ms_error_bound(a.sc, a.c_rel, a.Tq, a.d, sum_norm * 1.000001);
+    const int kk = (int)min((long long)a.k, a.nc);
+    const bool skip = (double)a.cand_key[f * a.nc + slot] > (double)a.cand_key[f * a.nc + kk - 1] + 2.0 * E;
+    __syncthreads();                               // s_max is reused below
+    if (skip) {
+      if (threadIdx.x == 0) a.out[f * a.nc + slot] = -NINF;
+      return;
+    }
+  }
   const int groups = (a.Tq + 31) / 32;
   for (int tg = 0; tg < groups; ++tg) {
     const int t = tg * 32 + lane;
@@ -305,17 +342,17 @@ ms_final_kernel(const MsFinal a) {
     double kv = INF; long long id = 0x7fffffffffffffffLL;
     if (i < a.nc) {
       const long long cid = a.cand_id[q * a.nc + i];
-      if (cid >= 0) { kv = a.exact[q * a.nc + i]; id = cid; if (kv != kv) kv = INF; }
+      if (cid >= 0) {
+        kv = a.exact[q * a.nc + i];
+        if (kv != kv) kv = INF;
+        if (kv < INF) id = cid;                      // (+inf: outside the band, not scored; empty documents)
+      }
     }
     s_key[i] = kv; s_id[i] = id;
   }
   __syncthreads();
   const double sum_norm = (double)s_red[0] + s_red[1] + s_red[2] + s_red[3];
-  int sq, sb;
-  direct_exps(NWK_METRIC_DOT, a.sc, sq, sb);
-  const double dmax = sqrt((double)__uint_as_float(a.sc->bn2max));
-  const double E = ((double)a.c_rel * dmax + ldexp(1.0, -25 - sb) * sqrt((double)a.d) + 4e-6 * dmax) * sum_norm +
-                   a.Tq * ldexp(1.0, -25 - sq) * sqrt((double)a.d) * dmax + 1e-30;
+  const double E = ms_error_bound(a.sc, a.c_rel, a.Tq, a.d, sum_norm * 1.000001);
   // monitor: the approximate scores must lie within E of the exact ones
   float ratio = 0.f;
   for (int i = threadIdx.x; i < a.nc; i += blockDim.x) {
@@ -462,12 +499,14 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
     ex_optin = ex_smem;
   }
+  const float c_rel = (float)(1.0 / 1024.0 * 1.001 + ((double)d / 16.0 + 2.0) / 4194304.0);
   MsExact e{};
   e.qtok = qtok; e.docs = docs; e.doc_len = doc_len; e.nq = nq; e.nd = nd; e.Tq = Tq; e.Td = Td; e.d = d;
   for (long long q0 = 0; q0 < nq; q0 += 32768) {
     const long long nf = std::min<long long>(32768, nq - q0);
     MsExact es = e;
     es.qtok = qtok + q0 * Tq * d; es.cand = cand_id + q0 * pl.nc; es.nc = pl.nc; es.out = exact + q0 * pl.nc;
+    es.cand_key = cand_key + q0 * pl.nc; es.k = k; es.sc = sc; es.c_rel = c_rel;
     ms_exact_kernel<<<dim3((unsigned)pl.nc, (unsigned)nf), 256, ex_smem, s>>>(es);
     NWK_LAUNCH_CHECK();
   }
@@ -475,7 +514,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   f.qtok = qtok; f.nq = nq; f.Tq = Tq; f.d = d; f.k = k; f.nc = pl.nc; f.nd = nd; f.cand_key = cand_key; f.cand_id = cand_id;
   f.exact = exact; f.sc = sc; f.scw = sc; f.id_offset = id_offset; f.out_score = out_score; f.out_idx = out_idx;
   f.fail_list = fail_list;
-  f.c_rel = (float)(1.0 / 1024.0 * 1.001 + ((double)d / 16.0 + 2.0) / 4194304.0);
+  f.c_rel = c_rel;
   ms_final_kernel<<<(unsigned)nq, 128, 0, s>>>(f);
   NWK_LAUNCH_CHECK();
 

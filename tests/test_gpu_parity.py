@@ -533,3 +533,35 @@ def test_maxsim_parity(cuda_device, nq, tq, nd, td, d, k, ragged):
     for r, c in mism:                                           # only exact ties may swap
         assert abs(full[r, got_i[r, c] - 3] - t_s[r, c]) <= 1e-6 * max(1.0, abs(t_s[r, c])), (r, c)
     print((nq, tq, nd, td, d, k, ragged), st, len(mism))
+
+
+def test_maxsim_uncertified_queries_are_rescored_exactly(cuda_device):
+    """Every document occurs 700 times: far more than the 256 candidates tie with the k-th score, no
+    query can be certified, and all of them must be re-scored against every document (ids in order)."""
+    import torch
+    from oracle import maxsim_oracle as mso
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(3)
+    uniq = rng.standard_normal((3, 40, 64)).astype(np.float32)
+    dt = np.tile(uniq, (700, 1, 1))                            # 2100 documents, each one of 3
+    qt = rng.standard_normal((7, 32, 64)).astype(np.float32)
+    got_s, got_i = knn.maxsim_topk(torch.from_numpy(qt).to(cuda_device), torch.from_numpy(dt).to(cuda_device), 20)
+    st = dict(knn.last_stats)
+    assert st["n_fallback_queries"] == 7, st
+    t_s, t_i = mso.maxsim_topk_f64(qt, dt, 20)
+    np.testing.assert_array_equal(got_i.cpu().numpy(), t_i)
+    np.testing.assert_allclose(got_s.cpu().numpy(), t_s, rtol=1e-5, atol=1e-6)
+
+
+def test_maxsim_error_behaviour(cuda_device):
+    import torch
+    from neighborhoodwatch_b200 import knn
+    from neighborhoodwatch_b200._native import NwkError
+    q = torch.zeros((2, 24, 64), device=cuda_device)           # 24 tokens: not a power of two
+    d = torch.zeros((50, 40, 64), device=cuda_device)
+    with pytest.raises(NwkError):
+        knn.maxsim_topk(q, d, 5)
+    with pytest.raises(AssertionError):
+        knn.maxsim_topk(torch.zeros((2, 32, 64), device=cuda_device), d, 51)
+    with pytest.raises(RuntimeError):
+        knn.maxsim_topk(torch.zeros((2, 32, 64)), d.cpu(), 5)
