@@ -74,14 +74,28 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [ACC_STAGES]
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* afull_bar = bars + 2 * STAGES + 2 * ACC_STAGES;        // [2] resident query tile buffers
+  uint64_t* aempty_bar = bars + 2 * STAGES + 2 * ACC_STAGES + 2;   // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stage_bytes = STAGE_A_BYTES + p.N * 128;
+  // The query tile stays resident for a whole unit (G documents), like tc_kernel's ARES variant: the
+  // ring then carries document stages only (N x 128 bytes per K-block instead of 16 KB more), which is
+  // what keeps a 128 x 192 x 128 tile (768 clk of MMAs) inside the 64 B/clk an SM can take from L2.
+  // Rows too long for that (more than 6 K-blocks) stream the query tile with every document.
+  const bool ares = p.nKB <= 6;
+  const int a_bytes = p.nKB * STAGE_A_BYTES;
+  const int nA = ares ? ((2 * a_bytes + 4 * STAGE_B_BYTES <= STAGES * STAGE_BYTES) ? 2 : 1) : 0;
+  const int nsb = ares ? min(STAGES, (STAGES * STAGE_BYTES - nA * a_bytes) / STAGE_B_BYTES) : STAGES;
+  unsigned char* const b_ring = smem + nA * a_bytes;
+  const int stage_bytes = (ares ? 0 : STAGE_A_BYTES) + p.N * 128;
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_q); ptx::prefetch_tensormap(&tmap_d); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4);
+      ptx::mbar_init(&afull_bar[a], 1); ptx::mbar_init(&aempty_bar[a], 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) { ptx::tmem_alloc(s_tmem, ACC_STAGES * TB); ptx::tmem_relinquish(); }
@@ -101,31 +115,50 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
+    int abuf = 0; uint32_t aphase = 0;
     bool ok = true;
     for (int u = blockIdx.x; ok && u < p.nUnits; u += gridDim.x) {
       int qt, len; long long doc0;
       unit(u, qt, doc0, len);
+      if (ares) {
+        if (!ptx::mbar_wait(&aempty_bar[abuf], aphase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&afull_bar[abuf], a_bytes);
+          for (int kb = 0; kb < p.nKB; ++kb)
+            ptx::tma_load_2d(smem + abuf * a_bytes + kb * STAGE_A_BYTES, &tmap_q, &afull_bar[abuf], kb * BK, qt * TQ);
+        }
+        __syncwarp();
+        if (++abuf == nA) { abuf = 0; aphase ^= 1; }
+      }
       for (int i = 0; ok && i < len; ++i)
         for (int kb = 0; kb < p.nKB; ++kb) {
           if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, ERR_PRODUCER)) { ok = false; break; }
           if (ptx::elect_one()) {
-            unsigned char* sa = smem + stage * STAGE_BYTES;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * BK, qt * TQ);
-            ptx::tma_load_2d(sa + STAGE_A_BYTES, &tmap_d, &full_bar[stage], kb * BK, (int)((doc0 + i) * p.N));
+            if (ares) {
+              ptx::tma_load_2d(b_ring + stage * STAGE_B_BYTES, &tmap_d, &full_bar[stage], kb * BK, (int)((doc0 + i) * p.N));
+            } else {
+              unsigned char* sa = smem + stage * STAGE_BYTES;
+              ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * BK, qt * TQ);
+              ptx::tma_load_2d(sa + STAGE_A_BYTES, &tmap_d, &full_bar[stage], kb * BK, (int)((doc0 + i) * p.N));
+            }
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nsb) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t idesc = ptx::umma_idesc_f16(TQ, p.N);
+    int abuf = 0; uint32_t aphase = 0;
     bool ok = true;
     for (int u = blockIdx.x; ok && u < p.nUnits; u += gridDim.x) {
       int qt, len; long long doc0;
       unit(u, qt, doc0, len);
+      if (ares) {
+        if (!ptx::mbar_wait(&afull_bar[abuf], aphase, p.err, ERR_MMA_FULL)) { ok = false; break; }
+      }
       for (int i = 0; ok && i < len; ++i) {
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, ERR_MMA_EMPTY)) { ok = false; break; }
         ptx::tc_fence_after();
@@ -134,9 +167,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (!ptx::mbar_wait(&full_bar[stage], phase, p.err, ERR_MMA_FULL)) { ok = false; break; }
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sa = ares ? ptx::smem_u32(smem + abuf * a_bytes + kb * STAGE_A_BYTES)
+                                     : ptx::smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t da = ptx::umma_desc_sw128(sa);
-            const uint64_t db = ptx::umma_desc_sw128(sa + STAGE_A_BYTES);
+            const uint64_t db = ptx::umma_desc_sw128(ares ? ptx::smem_u32(b_ring + stage * STAGE_B_BYTES) : sa + STAGE_A_BYTES);
             const int nk = (kb == p.nKB - 1) ? p.kLast : BK / 16;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
@@ -144,13 +178,17 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             ptx::tc_commit(&empty_bar[stage]);
-            if (kb == p.nKB - 1) ptx::tc_commit(&tfull_bar[acc]);
+            if (kb == p.nKB - 1) {
+              ptx::tc_commit(&tfull_bar[acc]);
+              if (ares && i == len - 1) ptx::tc_commit(&aempty_bar[abuf]);   // the unit's MMAs are all issued
+            }
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nsb) { stage = 0; phase ^= 1; }
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      if (ares) { if (++abuf == nA) { abuf = 0; aphase ^= 1; } }
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread <-> TMEM lane <-> query-token row of the tile =====
@@ -219,7 +257,7 @@ __device__ __forceinline__ double ms_error_bound(const Scalars* sc, float c_rel,
 }
 
 // exact fp64 MaxSim of (query, document) pairs: grid (pairs per query, queries); lane = query token,
-// warp = document tokens j = warp, warp + 8, ...; the query sits transposed in shared memory.
+// warp = document tokens j = warp, warp + 8, ... of a tile.
 struct MsExact {
   const float* qtok; const float* docs; const int* doc_len;
   long long nq, nd; int Tq, Td, d;
@@ -232,12 +270,15 @@ struct MsExact {
   const float* cand_key; int k; const Scalars* sc; float c_rel;
 };
 
+// The document is staged tile by tile (tj tokens) in shared memory as doubles, converted once for all
+// query tokens; lane = query token keeps 8 of its components as doubles in registers per pass and
+// one accumulator per document token of its warp (tj / 8 of them), so the inner loop is one
+// broadcast LDS.128 per two DFMAs and no conversions.
 __global__ void __launch_bounds__(256)
-ms_exact_kernel(const MsExact a) {
-  extern __shared__ float ms_smem[];
-  float* s_qT = ms_smem;                           // [d][Tq]
-  float* s_doc = ms_smem + (size_t)a.d * a.Tq;     // [8][d]  one document token per warp
-  double* s_max = reinterpret_cast<double*>(s_doc + 8 * a.d);     // [8][Tq]
+ms_exact_kernel(const MsExact a, const int tj) {
+  extern __shared__ __align__(16) unsigned char msx_smem[];
+  double* s_doc = reinterpret_cast<double*>(msx_smem);                  // [tj][d]
+  double* s_max = s_doc + (size_t)tj * a.d;                             // [8][Tq]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long f = blockIdx.y;
   const long long q = a.qsel ? a.qsel[f] : f;
@@ -248,18 +289,14 @@ ms_exact_kernel(const MsExact a) {
     if (threadIdx.x == 0) a.out[f * a.nc + slot] = -NINF;          // padding candidate: +inf key
     return;
   }
-  for (int e = threadIdx.x; e < a.Tq * a.d; e += blockDim.x) {
-    const int t = e / a.d, c = e - t * a.d;
-    s_qT[c * a.Tq + t] = a.qtok[(q * a.Tq + t) * a.d + c];
-  }
+  const float* qrow0 = a.qtok + q * a.Tq * a.d;
   const int valid = a.doc_len ? max(0, min(a.doc_len[doc], a.Td)) : a.Td;
-  __syncthreads();
   if (a.cand_key) {
-    // sum_t |q_t| from the transposed copy (warp w: tokens w, w + 8, ...), then the band test
+    // sum_t |q_t| (warp w: tokens w, w + 8, ...), then the band test
     double sn = 0.0;
     for (int t = warp; t < a.Tq; t += 8) {
       float n2 = 0.f;
-      for (int c = lane; c < a.d; c += 32) { const float v = s_qT[c * a.Tq + t]; n2 = fmaf(v, v, n2); }
+      for (int c = lane; c < a.d; c += 32) { const float v = qrow0[t * a.d + c]; n2 = fmaf(v, v, n2); }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
       sn += sqrt((double)n2);
@@ -277,21 +314,62 @@ ms_exact_kernel(const MsExact a) {
       return;
     }
   }
+  constexpr int MAXG = 4;                          // Tq <= 128: up to four tokens per lane
   const int groups = (a.Tq + 31) / 32;
-  for (int tg = 0; tg < groups; ++tg) {
-    const int t = tg * 32 + lane;
-    double best = NINF;
-    for (int j = warp; j < valid; j += 8) {
-      __syncwarp();
-      for (int c = lane; c < a.d; c += 32) s_doc[warp * a.d + c] = a.docs[(doc * a.Td + j) * a.d + c];
-      __syncwarp();
-      if (t < a.Tq) {
-        double acc = 0.0;
-        for (int c = 0; c < a.d; ++c) acc = fma((double)s_qT[c * a.Tq + t], (double)s_doc[warp * a.d + c], acc);
-        best = fmax(best, acc);
+  const int per_warp = tj / 8;                     // document tokens of a tile per warp (<= 8)
+  double best[MAXG];
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) best[g] = NINF;
+  for (int tile0 = 0; tile0 < valid; tile0 += tj) {
+    const int nt = min(tj, valid - tile0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nt * a.d; e += blockDim.x)
+      s_doc[e] = (double)a.docs[(doc * a.Td + tile0) * a.d + e];
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) {
+      if (g >= groups) break;
+      const int t = g * 32 + lane;
+      const float* qrow = qrow0 + (long long)min(t, a.Tq - 1) * a.d;
+      double acc[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
+      for (int cb = 0; cb < a.d; cb += 8) {
+        double q8[8];
+        const float4 qa = *reinterpret_cast<const float4*>(qrow + cb);
+        float4 qb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb + 4 < a.d) qb = *reinterpret_cast<const float4*>(qrow + cb + 4);
+        q8[0] = qa.x; q8[1] = qa.y; q8[2] = qa.z; q8[3] = qa.w; q8[4] = qb.x; q8[5] = qb.y; q8[6] = qb.z; q8[7] = qb.w;
+        const int nc8 = min(8, a.d - cb);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (jj >= per_warp) break;
+          const int j = warp + 8 * jj;                 // token inside the tile (warp-uniform)
+          if (j < nt) {
+            const double* dv = s_doc + (size_t)j * a.d + cb;
+            if (nc8 == 8) {
+#pragma unroll
+              for (int c = 0; c < 8; c += 2) {
+                const double2 d2 = *reinterpret_cast<const double2*>(dv + c);
+                acc[jj] = fma(q8[c], d2.x, acc[jj]);
+                acc[jj] = fma(q8[c + 1], d2.y, acc[jj]);
+              }
+            } else {
+              for (int c = 0; c < nc8; ++c) acc[jj] = fma(q8[c], dv[c], acc[jj]);
+            }
+          }
+        }
       }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (jj < per_warp && warp + 8 * jj < nt) best[g] = fmax(best[g], acc[jj]);
     }
-    if (t < a.Tq) s_max[warp * a.Tq + t] = best;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    const int t = g * 32 + lane;
+    if (g < groups && t < a.Tq) s_max[warp * a.Tq + t] = best[g];
   }
   __syncthreads();
   if (warp == 0) {
@@ -461,6 +539,10 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   const size_t tws_bytes = ws_bytes - ar.off;
   const long long launches0 = g_launches.load();
 
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&ev[i]);
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]); } } ev_guard{ev};
+  cudaEventRecord(ev[0], s);
   NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
   qmax_kernel<<<sms, 256, 0, s>>>(qtok, nq * Tq * d, &sc->qabsmax);
   NWK_LAUNCH_CHECK();
@@ -474,6 +556,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     ms_docprep_kernel<<<(unsigned)blocks, 256, 0, s>>>(docs, nd, Td, pl.N, d, pl.pitch, sc, dhh);
     NWK_LAUNCH_CHECK();
   }
+  cudaEventRecord(ev[1], s);
   CUtensorMap tm_q, tm_d;
   NWK_TRY(make_tmap(&tm_q, qh, nq * Tq, pl.dh, true, TQ, pl.pitch));
   NWK_TRY(make_tmap(&tm_d, dhh, nd * pl.N, pl.dh, true, pl.N, pl.pitch));
@@ -491,9 +574,14 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     maxsim_kernel<<<pl.nUnits < sms ? pl.nUnits : sms, MS_THREADS, smem, s>>>(tm_q, tm_d, p);
     NWK_LAUNCH_CHECK();
   }
+  cudaEventRecord(ev[2], s);
   NWK_TRY(topk_from_keys(neg, nd, nd, nq, (int)pl.nc, nullptr, 0, cand_key, cand_id, tws, tws_bytes, s));
+  cudaEventRecord(ev[3], s);
 
-  const int ex_smem = (d * Tq + 8 * d) * 4 + 8 * Tq * 8;
+  // document tile of the exact kernel: tj tokens as doubles, about 64 KB
+  int tj = (64 * 1024 / (d * 8)) / 8 * 8;
+  tj = tj < 8 ? 8 : (tj > 64 ? 64 : tj);
+  const int ex_smem = tj * d * 8 + 8 * Tq * 8 + 64;
   static int ex_optin = 48 * 1024;
   if (ex_smem > ex_optin) {
     NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
@@ -507,7 +595,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     MsExact es = e;
     es.qtok = qtok + q0 * Tq * d; es.cand = cand_id + q0 * pl.nc; es.nc = pl.nc; es.out = exact + q0 * pl.nc;
     es.cand_key = cand_key + q0 * pl.nc; es.k = k; es.sc = sc; es.c_rel = c_rel;
-    ms_exact_kernel<<<dim3((unsigned)pl.nc, (unsigned)nf), 256, ex_smem, s>>>(es);
+    ms_exact_kernel<<<dim3((unsigned)pl.nc, (unsigned)nf), 256, ex_smem, s>>>(es, tj);
     NWK_LAUNCH_CHECK();
   }
   MsFinal f{};
@@ -517,6 +605,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   f.c_rel = c_rel;
   ms_final_kernel<<<(unsigned)nq, 128, 0, s>>>(f);
   NWK_LAUNCH_CHECK();
+  cudaEventRecord(ev[4], s);
 
   Scalars h{};
   NWK_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
@@ -530,15 +619,24 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     const long long nf = std::min<long long>(pl.fb_rows, h.fail_cnt - done);
     MsExact es = e;
     es.qsel = fail_list + done; es.cand = nullptr; es.nc = nd; es.out = fb;
-    ms_exact_kernel<<<dim3((unsigned)nd, (unsigned)nf), 256, ex_smem, s>>>(es);
+    ms_exact_kernel<<<dim3((unsigned)nd, (unsigned)nf), 256, ex_smem, s>>>(es, tj);
     NWK_LAUNCH_CHECK();
     NWK_TRY(topk_from_keys(fb, nd, nd, nf, k, fail_list + done, id_offset, out_score, out_idx, tws, tws_bytes, s));
     ms_negate_rows_kernel<<<(unsigned)((nf * k + 255) / 256), 256, 0, s>>>(out_score, fail_list + done, (int)nf, k);
     NWK_LAUNCH_CHECK();
   }
+  cudaEventRecord(ev[5], s);
   NWK_CUDA(cudaStreamSynchronize(s));
   if (stats) {
     memset(stats, 0, sizeof(*stats));
+    // stages of this path: prep = fp16 copies, filter = the tcgen05 GEMM with the fused max / sum,
+    // sample = top-4k of the approximate scores, finish = exact re-scoring + ordering, fallback
+    cudaEventElapsedTime(&stats->ms_prep, ev[0], ev[1]);
+    cudaEventElapsedTime(&stats->ms_filter, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->ms_sample, ev[2], ev[3]);
+    cudaEventElapsedTime(&stats->ms_finish, ev[3], ev[4]);
+    cudaEventElapsedTime(&stats->ms_fallback, ev[4], ev[5]);
+    cudaEventElapsedTime(&stats->ms_total, ev[0], ev[5]);
     stats->path = 3;
     stats->n_fallback_queries = h.fail_cnt;
     stats->max_candidates = (int)pl.nc;
