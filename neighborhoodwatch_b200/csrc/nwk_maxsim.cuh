@@ -31,7 +31,7 @@ struct MsParams {
   int* err;
 };
 
-constexpr int MS_THREADS = 256;   // 4 control warps + 1 epilogue warpgroup
+constexpr int MS_THREADS = 384;   // 4 control warps + 2 epilogue warpgroups that take the tiles (= accumulator stages) in turn
 
 // documents -> fp16 rows [nd * N][pitch]: token j of document i at row i * N + j, rows j >= Td zero;
 // max |d|^2 over all tokens for the error bound.  One warp per output row.
@@ -191,11 +191,16 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (ares) { if (++abuf == nA) { abuf = 0; aphase ^= 1; } }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread <-> TMEM lane <-> query-token row of the tile =====
+    // ===== epilogue: thread <-> TMEM lane <-> query-token row of the tile.  Two warpgroups, each
+    // bound to one accumulator stage: warpgroup g takes every second tile whole (all N columns), so
+    // a row's maximum never has to be combined across warpgroups and each has two MMA tile times
+    // for its tile (one warpgroup alone, 6 x (load + 16 dependent FMNMX3), took longer than the
+    // 768 clk of a tile's MMAs). =====
     const int quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const float NINF = __int_as_float(0xff800000);
-    int acc = 0; uint32_t acc_phase = 0;
+    int ti = 0;                                                     // tiles this CTA has walked
     int sq, sb;
     direct_exps(NWK_METRIC_DOT, p.sc, sq, sb);
     const double unscale = (double)pow2f(-(sq + sb));
@@ -206,29 +211,45 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const long long row = (long long)qt * TQ + row_in_tile;     // query-token row
       const long long q = row / p.Tq;
       for (int i = 0; ok && i < len; ++i) {
+        const int acc = ti & 1;
+        const uint32_t acc_phase = (ti >> 1) & 1;
+        ++ti;
+        if (acc != wg) continue;
         const long long doc = doc0 + i;
         if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, ERR_EPI)) { ok = false; break; }
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TB;
         const int valid = p.doc_len ? max(0, min(p.doc_len[doc], p.Td)) : p.Td;    // warp-uniform
-        float m = NINF;
-        uint32_t v[32];
-        for (int ch = 0; ch * 32 < valid; ++ch) {
-          ptx::tmem_ld_32x32(taddr + ch * 32, v);
-          ptx::tmem_wait_ld();
-          const int left = valid - ch * 32;
+        const int nch = (valid + 31) >> 5;
+        float m0 = NINF, m1 = NINF;
+        uint32_t va[32], vb[32];
+        auto fold = [&](const uint32_t (&v)[32], const int left) {
           if (left >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            for (int j = 0; j < 32; j += 4) {
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+              m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < left) m = fmaxf(m, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) if (j < left) m0 = fmaxf(m0, __uint_as_float(v[j]));
+          }
+        };
+        if (nch > 0) ptx::tmem_ld_32x32(taddr, va);
+        for (int ch = 0; ch < nch; ch += 2) {
+          ptx::tmem_wait_ld();
+          if (ch + 1 < nch) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, vb);
+          fold(va, valid - ch * 32);
+          if (ch + 1 < nch) {
+            ptx::tmem_wait_ld();
+            if (ch + 2 < nch) ptx::tmem_ld_32x32(taddr + (ch + 2) * 32, va);
+            fold(vb, valid - (ch + 1) * 32);
           }
         }
+        float m = fmaxf(m0, m1);
         __syncwarp();
         ptx::tc_fence_before();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         // sum over the query's token rows (Tq a power of two): inside the warp, and across warps by atomics
         const int span = min(p.Tq, 32);
         for (int o = span >> 1; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
