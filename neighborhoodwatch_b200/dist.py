@@ -67,3 +67,30 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
         return d_loc, i_loc
     all_d, all_i = gather_partials(d_loc, i_loc, group)
     return merge(all_d, all_i, k)
+
+
+def sharded_maxsim(query_tokens: torch.Tensor, local_doc_tokens: torch.Tensor, k: int, doc_offset: int,
+                   doc_len: Optional[torch.Tensor] = None, group=None, local_maxsim: Optional[Callable] = None,
+                   merge: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Document-level MaxSim when every rank holds a shard of the documents: local top-k with global
+    document ids (``id_offset = doc_offset``), one all-gather, merge by (score descending, id) --
+    the kNN reducer applied to the negated scores.  Shards smaller than k are padded (-inf / -1)."""
+    if local_maxsim is None or merge is None:
+        from . import knn as _knn
+        local_maxsim = local_maxsim or (lambda q, dd, kk, dl, off: _knn.maxsim_topk(q, dd, kk, doc_len=dl, id_offset=off))
+        merge = merge or _knn.merge_topk
+    nq = query_tokens.shape[0]
+    kk = min(k, local_doc_tokens.shape[0])
+    if kk > 0:
+        s_loc, i_loc = local_maxsim(query_tokens, local_doc_tokens, kk, doc_len, doc_offset)
+    else:
+        s_loc = torch.empty((nq, 0), dtype=torch.float32, device=query_tokens.device)
+        i_loc = torch.empty((nq, 0), dtype=torch.int64, device=query_tokens.device)
+    if kk < k:
+        s_loc = torch.cat([s_loc, torch.full((nq, k - kk), float("-inf"), dtype=s_loc.dtype, device=s_loc.device)], dim=1)
+        i_loc = torch.cat([i_loc, torch.full((nq, k - kk), -1, dtype=i_loc.dtype, device=i_loc.device)], dim=1)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return s_loc, i_loc
+    all_d, all_i = gather_partials(-s_loc, i_loc, group)          # distances = negated scores
+    m_d, m_i = merge(all_d, all_i, k)
+    return -m_d, m_i

@@ -193,3 +193,48 @@ def test_sharded_knn_gloo_world2(tmp_path, nb, k):
         g = np.load(tmp_path / f"r{r}.npz")
         np.testing.assert_array_equal(g["i"], t_i)
         np.testing.assert_array_equal(g["d"], t_d)
+
+
+def _maxsim_worker(rank, world, port, nd, nq, k, out_dir):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import maxsim_oracle as mso
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        qt = rng.standard_normal((nq, 8, 16)).astype(np.float32)
+        dt = rng.standard_normal((nd, 12, 16)).astype(np.float32)
+        lo, hi = nwdist.shard_bounds(nd, world, rank)
+
+        def local_maxsim(q, dd, kk, dl, off):       # CPU stand-in for the kernel (test only)
+            ss, ii = mso.maxsim_topk_f64(q.numpy(), dd.numpy(), kk)
+            return torch.from_numpy(ss.astype(np.float32)), torch.from_numpy(ii + off)
+
+        def merge_fn(all_d, all_i, kk):
+            md, mi = mo.merge_by_distance_then_index([(all_d[p].numpy(), all_i[p].numpy()) for p in range(all_d.shape[0])], kk)
+            return torch.from_numpy(md), torch.from_numpy(mi)
+
+        out_s, out_i = nwdist.sharded_maxsim(torch.from_numpy(qt), torch.from_numpy(dt[lo:hi]), k, lo,
+                                             local_maxsim=local_maxsim, merge=merge_fn)
+        np.savez(os.path.join(out_dir, f"m{rank}.npz"), s=out_s.numpy(), i=out_i.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nd,k", [(301, 10), (13, 10)])
+def test_sharded_maxsim_gloo_world2(tmp_path, nd, k):
+    """Documents sharded over two ranks: local top-k with global ids, all-gather, merge of the negated
+    scores -- identical on both ranks and equal to the single-device answer."""
+    from oracle import maxsim_oracle as mso
+    nq = 9
+    port = _free_port()
+    mp.spawn(_maxsim_worker, args=(2, port, nd, nq, k, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    qt = rng.standard_normal((nq, 8, 16)).astype(np.float32)
+    dt = rng.standard_normal((nd, 12, 16)).astype(np.float32)
+    t_s, t_i = mso.maxsim_topk_f64(qt, dt, k)
+    for r in range(2):
+        g = np.load(tmp_path / f"m{r}.npz")
+        np.testing.assert_array_equal(g["i"], t_i)
+        np.testing.assert_allclose(g["s"], t_s, rtol=1e-6)
