@@ -565,3 +565,26 @@ def test_maxsim_error_behaviour(cuda_device):
         knn.maxsim_topk(torch.zeros((2, 32, 64), device=cuda_device), d, 51)
     with pytest.raises(RuntimeError):
         knn.maxsim_topk(torch.zeros((2, 32, 64)), d.cpu(), 5)
+
+
+def test_maxsim_shards_merge_to_the_one_shot_result(cuda_device):
+    """Documents split into three shards (global ids through id_offset), merged as negated scores by the
+    kNN reducer == the one-shot top-k (the multi-GPU path of dist.sharded_maxsim on one device)."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(21)
+    qt = torch.from_numpy(rng.standard_normal((16, 32, 128)).astype(np.float32)).to(cuda_device)
+    dt = torch.from_numpy(rng.standard_normal((900, 100, 128)).astype(np.float32)).to(cuda_device)
+    one_s, one_i = knn.maxsim_topk(qt, dt, 50)
+    parts = [knn.maxsim_topk(qt, dt[lo:lo + 300], 50, id_offset=lo) for lo in range(0, 900, 300)]
+    m_d, m_i = knn.merge_topk(torch.stack([-p[0] for p in parts]), torch.stack([p[1] for p in parts]), 50)
+    assert torch.equal(-m_d, one_s)
+    # the merge orders by (fp32 score, id), the one-shot result by (fp64 score, id): ids may differ only
+    # inside runs of fp32-equal scores, and each row must hold the same id set
+    assert torch.equal(torch.sort(m_i, dim=1).values, torch.sort(one_i, dim=1).values)
+    diff = m_i != one_i
+    left = torch.zeros_like(diff)
+    left[:, 1:] = m_d[:, 1:] == m_d[:, :-1]
+    right = torch.zeros_like(diff)
+    right[:, :-1] = m_d[:, :-1] == m_d[:, 1:]
+    assert bool(torch.all(~diff | left | right))
