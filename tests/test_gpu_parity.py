@@ -100,6 +100,8 @@ def test_tc_operand_rounding_probe(cuda_device):
     (64, 40000, 128, 256),       # k at the tensor-core path's limit
     (50, 3000, 4, 10),           # the shortest rows the tensor-core path takes: one K-block, one MMA step
     (70, 9000, 12, 20),          # (squared L2's extra columns share that block)
+    (1, 300, 8, 10),             # a single query against less than two tiles
+    (257, 70000, 256, 100),      # three query tiles, four K-blocks (+ one for squared L2's columns): one resident buffer
 ])
 def test_tc_knn_parity(cuda_device, metric, nq, nb, d, k):
     from neighborhoodwatch_b200 import knn
