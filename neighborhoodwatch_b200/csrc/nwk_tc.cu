@@ -505,6 +505,9 @@ struct Sched {
       i = 0;
     }
     out_qt = qt;
+    // (all CTAs on a chunk walk its tiles in the same order on purpose: requests for a tile that is
+    //  still on its way from HBM merge in L2; rotating the order per query tile was measured:
+    //  +2 % filter time at d = 768, +6 % at d = 1536)
     if (MODE == MODE_FILTER) out_t = c * G + i;
     else if (MODE == MODE_SAMPLE) out_t = c + i;
     else out_t = dump_t;

@@ -69,6 +69,70 @@ __global__ void __launch_bounds__(128, 1) k(int tiles, int nkb, int N, int nacc,
   if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
 }
 
+// The same MMAs fed through a 4-stage full / empty mbarrier ring by a producer warp (bulk copies of
+// `stage_kb` KB per K-block from an L2-resident buffer), both roles as converged warps with elect.sync:
+// the filter kernel's operand pipeline without its epilogue and schedule.
+__global__ void __launch_bounds__(128, 1) kring(int tiles, int nkb, int stage_kb, const unsigned char* src, long long* clk) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[4], empty[4], bar_done, bar_tile[2];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(&bar_done, 1); ptx::mbar_init(&bar_tile[0], 1); ptx::mbar_init(&bar_tile[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc(&s_tmem, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const int total = tiles * nkb;
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < total; ++i) {
+      while (!ptx::mbar_try_wait(&empty[stage], phase ^ 1)) {}
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full[stage], stage_kb * 1024);
+        ptx::bulk_load_1d(smem + stage * 48 * 1024, src + ((size_t)(blockIdx.x * 7 + i) % 2048) * 49152, stage_kb * 1024, &full[stage]);
+      }
+      __syncwarp();
+      if (++stage == 4) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+    const long long t0 = clock64();
+    int stage = 0; uint32_t phase = 0; int acc = 0;
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < nkb; ++kb) {
+        while (!ptx::mbar_try_wait(&full[stage], phase)) {}
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * 48 * 1024);
+          const uint64_t da = ptx::umma_desc_sw128(sa);
+          const uint64_t db = ptx::umma_desc_sw128(sa + 16 * 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) ptx::mma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+          ptx::tc_commit(&empty[stage]);
+          if (kb == nkb - 1) ptx::tc_commit(&bar_tile[acc]);
+        }
+        __syncwarp();
+        if (++stage == 4) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+    }
+    if (ptx::elect_one()) ptx::tc_commit(&bar_done);
+    __syncwarp();
+    while (!ptx::mbar_try_wait(&bar_done, 0)) {}
+    if (lane == 0) clk[blockIdx.x] = clock64() - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -98,5 +162,24 @@ int main() {
              grid * mmas * 128.0 * c.N * 16 * 2 / (ms * 1e-3) / 1e12);
     }
   }
+  cudaFuncSetAttribute(kring, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int nkb : {2, 12})
+    for (int kb : {16, 32, 48})
+      for (int grid : {1, sms}) {
+        const int tiles = 24000 / nkb;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float ms = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+          cudaEventRecord(e0);
+          kring<<<grid, 128, smem>>>(tiles, nkb, kb, src, clk);
+          cudaEventRecord(e1);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          cudaEventElapsedTime(&ms, e0, e1);
+        }
+        long long h; cudaMemcpy(&h, clk, 8, cudaMemcpyDeviceToHost);
+        printf("ring: nkb %2d, %2d KB per K-block, grid %3d: %.0f clk per tile (MMAs alone %d), %.2f GHz, %.0f GB/s per SM\n", nkb, kb,
+               grid, h / (double)tiles, nkb * 512, h / (ms * 1e6), (double)tiles * nkb * kb * 1024 / (ms * 1e-3) / 1e9);
+      }
   return 0;
 }
