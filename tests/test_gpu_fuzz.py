@@ -1,0 +1,18 @@
+"""Random shapes / metrics / data scales: the tensor-core path against the on-device fp64 scan.  -m gpu."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_shapes_equal_the_fp64_scan(cuda_device, seed):
+    """scripts/fuzz_shapes.py: 120 random (nq, nb, d, k, metric, data kind) combinations per seed -- every filter
+    variant, key form and plan the host picks -- must reproduce the fp64 scan bit for bit."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_shapes.py"), "120", str(seed)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
