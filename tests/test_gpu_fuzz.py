@@ -16,3 +16,10 @@ def test_random_shapes_equal_the_fp64_scan(cuda_device, seed):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_shapes.py"), "120", str(seed)],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_random_running_searches_equal_the_one_shot_result(cuda_device):
+    """scripts/fuzz_stream.py: random shapes, slab splits and arrival orders through nwk_topk_state_search."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_stream.py"), "100", "4"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
