@@ -23,3 +23,11 @@ def test_random_running_searches_equal_the_one_shot_result(cuda_device):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_stream.py"), "100", "4"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_random_maxsim_shapes_equal_the_oracle(cuda_device):
+    """scripts/fuzz_maxsim.py: random token counts (1..128 per query, 1..256 per document), dimensions, ragged
+    documents and query scales against oracle/maxsim_oracle.py."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_maxsim.py"), "30", "2"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
