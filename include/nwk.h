@@ -65,7 +65,7 @@ typedef enum nwk_metric {
 
 /* Per-call diagnostics (all counters refer to the last nwk_knn_f32 call they were passed to). */
 typedef struct nwk_knn_stats {
-  int32_t path;               /* 0 = fp64 exact scan; tcgen05 candidates + fp64 rerank: 1 = fp16, 2 = TF32 */
+  int32_t path;               /* 0 = fp64 exact scan; tcgen05 candidates + fp64 rerank: 1 = fp16, 2 = TF32; 3 = nwk_maxsim_f32 */
   int32_t n_fallback_queries; /* queries whose candidate set could not be certified -> fp64 exact scan   */
   int32_t max_candidates;     /* largest per-query candidate-log population seen                         */
   int32_t max_rerank;         /* largest per-query number of rows re-ranked in fp64                      */
