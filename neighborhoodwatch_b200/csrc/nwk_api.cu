@@ -298,9 +298,12 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
     c.init = true;
   }
   if (slab_rows <= 0) {
-    // >= 8 slabs so the first copy is a small part of the run, but slabs of at least 64K
-    // rows so the per-slab fixed cost stays negligible
-    slab_rows = (nb + 7) / 8;
+    // 8 slabs so the first copy is a small part of the run, but slabs of at least 64K rows so the
+    // per-slab fixed cost stays negligible.  That fixed cost is per QUERY (a sample pass and a
+    // finish stage per slab: 10-20 ms per slab at 100 000 queries, against 10 ms of exposed first
+    // copy per GB), so large query sets take fewer, larger slabs.
+    const long long want = nq > 50000 ? 3 : (nq > 20000 ? 4 : 8);
+    slab_rows = (nb + want - 1) / want;
     if (slab_rows < 65536) slab_rows = 65536;
     const long long max_rows = (long long)((6ull << 30) / ((size_t)d * 4));
     if (slab_rows > max_rows) slab_rows = max_rows;
