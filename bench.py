@@ -332,6 +332,17 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    # two more untimed steps after the rendezvous (the GPUs idled through the barrier and the NVML
+    # set-up: a 10-step multi-GPU run was once timed at +25 % because its first steps ran on
+    # clocks that had dropped), then the timed region starts from a barrier again
+    for _ in range(2):
+        step()
+    for v in stage_ms.values():
+        v.clear()
+    for key in agg:
+        agg[key] = 0
+    exch_events.clear()
+    barrier()
     launches0 = _native.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
