@@ -108,7 +108,8 @@ int64_t nwk_launch_count(void);
  * exact powers of two -- the significand width of TF32 -- or TF32 itself), every candidate
  * within a proven error bound of the k-th is re-ranked in fp64, and queries for which the
  * bound cannot be established are recomputed by an fp64 scan.  Ordering is by
- * (fp64 distance, index).  Fails with NWK_ERR_ARG when k > nb (the reference asserts
+ * (fp64 distance, index).  base / query pointers that are not 16-byte aligned are served by
+ * the fp64 scan (correct, slow).  Fails with NWK_ERR_ARG when k > nb (the reference asserts
  * ``k <= len(dataset)``, cu_knn.py:237) or k > NWK_MAX_K. */
 #define NWK_MAX_K 1024
 size_t nwk_knn_workspace_bytes(int64_t nb, int64_t nq, int32_t d, int32_t k, int32_t metric,
@@ -126,10 +127,26 @@ int nwk_knn_f32(const float* base, int64_t nb, const float* query, int64_t nq, i
  *   idx   [P, nq, k_in] int64 device, global row ids
  *   out_dist [nq, k_out] fp32, out_idx [nq, k_out] int64; requires k_out <= P*k_in
  *   workspace: nwk_merge_workspace_bytes(P, nq, k_in, k_out) bytes of device scratch */
+#define NWK_MERGE_MAX_K 2048
 size_t nwk_merge_workspace_bytes(int32_t P, int64_t nq, int32_t k_in, int32_t k_out);
 int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq, int32_t k_in,
                    int32_t k_out, float* out_dist, int64_t* out_idx, void* workspace,
                    size_t ws_bytes, void* stream);
+/* The same merge when the P lists are not one contiguous [P, nq, k_in] array.
+ *   _strided: list p is dist + p * dist_stride / idx + p * idx_stride (strides in ELEMENTS) -- the
+ *             chunks of a packed all-gather buffer [P][nq*k_in f32 | nq*k_in i64], so one
+ *             collective moves distances and ids together;
+ *   _ptrs:    list p is dist_ptrs[p] / idx_ptrs[p] (HOST arrays of P <= 16 device pointers): lists
+ *             that live in different allocations or in the memory of peer GPUs (the kernel then
+ *             reads them over NVLink: gather and merge are one kernel).
+ * Padding entries are those with a negative id (they come out as +inf / -1 again); entries with a
+ * real id keep it even when their distance is +inf or nan (ordered last).  k_out <= NWK_MERGE_MAX_K. */
+int nwk_merge_topk_strided(int32_t P, const float* dist, int64_t dist_stride, const int64_t* idx,
+                           int64_t idx_stride, int64_t nq, int32_t k_in, int32_t k_out, float* out_dist,
+                           int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream);
+int nwk_merge_topk_ptrs(int32_t P, const float* const* dist_ptrs, const int64_t* const* idx_ptrs, int64_t nq,
+                        int32_t k_in, int32_t k_out, float* out_dist, int64_t* out_idx, void* workspace,
+                        size_t ws_bytes, void* stream);
 
 /* Running per-query top-k across base slabs: the intended semantics of the streaming
  * driver, cu_knn_ds.py:181-239 (one global result over all base batches), and the
@@ -149,7 +166,10 @@ int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* 
 int nwk_topk_state_search(nwk_topk_state* st, const float* base, int64_t nb, const float* query, int32_t d,
                           int32_t metric, int64_t id_offset, void* workspace, size_t ws_bytes, uint32_t flags,
                           nwk_knn_stats* stats, void* stream);
+/* finalize() copies the current result to out_dist / out_idx (device or host memory, enqueued on
+ * `stream`); reset() empties the state on `stream` so the handle can serve the next run. */
 int nwk_topk_state_finalize(nwk_topk_state* st, float* out_dist, int64_t* out_idx, void* stream);
+int nwk_topk_state_reset(nwk_topk_state* st, void* stream);
 int nwk_topk_state_destroy(nwk_topk_state* st);
 
 /* Host-buffer entry point (what `e2e` in bench.py times): base and query are HOST
@@ -163,6 +183,15 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
                      int32_t d, int32_t k, int32_t metric, int64_t id_offset, int64_t slab_rows,
                      float* out_dist_host, int64_t* out_idx_host, uint32_t flags,
                      nwk_knn_stats* stats);
+/* The slab partition nwk_knn_host_f32 uses (pure arithmetic, no device needed): slabs 0 .. nslab-2
+ * hold *slab_rows rows, the last one *last_rows; every slab holds at least k rows (the reference
+ * asserts the same of its last batch, cu_knn.py:177 / cu_knn_ds.py:168 -- here a tail shorter than k
+ * is folded into the slab before it).  slab_rows_in == 0 picks the default. */
+int nwk_host_slab_plan(int64_t nb, int64_t nq, int32_t d, int32_t k, int64_t slab_rows_in,
+                       int64_t* slab_rows, int64_t* nslab, int64_t* last_rows);
+/* The host path keeps its device staging ring, workspace and running state per device between
+ * calls (no allocation once they have grown to the shapes in use); this frees them. */
+int nwk_host_release(void);
 
 /* Document-level ColBERT MaxSim (the reference's colbert_knn.py:62-126 stops at a
  * token-level kNN over the flattened token embeddings, which nwk_knn_f32 with NWK_METRIC_DOT covers):

@@ -20,7 +20,9 @@ FLAG_FORCE_EXACT_SCAN = 0x1
 FLAG_NO_FALLBACK = 0x2
 FLAG_PROFILE = 0x4
 FLAG_TF32 = 0x8
+FLAG_ALPHA_BETA = 0x10
 MAX_K = 1024
+MERGE_MAX_K = 2048
 
 # every symbol include/nwk.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTED_SYMBOLS = (
@@ -28,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "nwk_merge_workspace_bytes", "nwk_merge_topk", "nwk_topk_state_create", "nwk_topk_state_update",
     "nwk_topk_state_search", "nwk_topk_state_finalize", "nwk_topk_state_destroy", "nwk_knn_host_f32", "nwk_synth_fill",
     "nwk_debug_tc_tile", "nwk_validate_pairs", "nwk_maxsim_workspace_bytes", "nwk_maxsim_f32",
+    "nwk_merge_topk_strided", "nwk_merge_topk_ptrs", "nwk_topk_state_reset", "nwk_host_slab_plan", "nwk_host_release",
 )
 
 
@@ -81,6 +84,19 @@ def load() -> ctypes.CDLL:
     lib.nwk_merge_topk.restype = c_int32
     lib.nwk_merge_topk.argtypes = [c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_size_t, c_void_p]
+    lib.nwk_merge_topk_strided.restype = c_int32
+    lib.nwk_merge_topk_strided.argtypes = [c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.nwk_merge_topk_ptrs.restype = c_int32
+    lib.nwk_merge_topk_ptrs.argtypes = [c_int32, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int32, c_int32,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.nwk_topk_state_reset.restype = c_int32
+    lib.nwk_topk_state_reset.argtypes = [c_void_p, c_void_p]
+    lib.nwk_host_slab_plan.restype = c_int32
+    lib.nwk_host_slab_plan.argtypes = [c_int64, c_int64, c_int32, c_int32, c_int64, POINTER(c_int64), POINTER(c_int64),
+                                       POINTER(c_int64)]
+    lib.nwk_host_release.restype = c_int32
+    lib.nwk_host_release.argtypes = []
     lib.nwk_topk_state_create.restype = c_int32
     lib.nwk_topk_state_create.argtypes = [c_int64, c_int32, POINTER(c_void_p)]
     lib.nwk_topk_state_update.restype = c_int32

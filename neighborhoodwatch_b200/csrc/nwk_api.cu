@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "nwk_common.cuh"
@@ -16,6 +17,11 @@ size_t exact_scan_workspace_bytes(long long nb, long long nsel, int k);
 size_t merge_workspace_bytes(int P, long long nq, int k_in, int k_out);
 int merge_topk(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
                float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+int merge_topk_strided(int P, const float* dist, long long dist_stride, const long long* idx, long long idx_stride,
+                       long long nq, int k_in, int k_out, float* out_dist, long long* out_idx, void* ws,
+                       size_t ws_bytes, cudaStream_t s);
+int merge_topk_ptrs(int P, const float* const* dist, const long long* const* idx, long long nq, int k_in, int k_out,
+                    float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
 bool tc_path_supported(long long nb, long long nq, int d, int k);
 size_t tc_workspace_bytes(long long nb, long long nq, int d, int k);
 int tc_knn(const float* base, long long nb, const float* query, long long nq, int d, int k, int metric,
@@ -50,28 +56,49 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-static int g_sm_count = 0;
+static DevState g_dev[NWK_MAX_DEVICES];
+static std::mutex g_dev_mu;
 
 int device_check() {
-  static int cached = -1;      // -1 unknown, 0 ok
-  if (cached == 0) return NWK_OK;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess)
     return fail(NWK_ERR_DEVICE, "no CUDA device available: %s (this library has no CPU fallback)",
                 cudaGetErrorString(e));
+  if (dev < 0 || dev >= NWK_MAX_DEVICES) return fail(NWK_ERR_DEVICE, "device ordinal %d out of range", dev);
+  DevState& st = g_dev[dev];
+  if (st.checked) return NWK_OK;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (st.checked) return NWK_OK;
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) return fail(NWK_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10)
     return fail(NWK_ERR_DEVICE, "device %d (%s) is sm_%d%d; libnwk is built for sm_100a only", dev, prop.name,
                 prop.major, prop.minor);
-  g_sm_count = prop.multiProcessorCount;
-  cached = 0;
+  st.sms = prop.multiProcessorCount;
+  for (int i = 0; i < NWK_SIDE_STREAMS; ++i) {
+    NWK_CUDA(cudaStreamCreateWithFlags(&st.side[i], cudaStreamNonBlocking));
+    NWK_CUDA(cudaEventCreateWithFlags(&st.ev_join[i], cudaEventDisableTiming));
+  }
+  NWK_CUDA(cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 16; ++i) NWK_CUDA(cudaEventCreateWithFlags(&st.ev_chunk[i], cudaEventDisableTiming));
+  st.checked = 1;
   return NWK_OK;
 }
 
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+// (callers have passed device_check() on this device)
+DevState* dev_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= NWK_MAX_DEVICES) dev = 0;
+  return &g_dev[dev];
+}
+
+int sm_count() {
+  const int n = dev_state()->sms;
+  return n > 0 ? n : 148;
+}
 
 static bool want_tc(long long nb, long long nq, int d, int k, unsigned int flags) {
   if (flags & NWK_FLAG_FORCE_EXACT_SCAN) return false;
@@ -90,33 +117,40 @@ __global__ void state_init_kernel(float* d, long long* i, long long n) {
   }
 }
 
-// Process-wide cache of the device staging buffers so repeated calls do not pay cudaMalloc.
+// Per-device cache of the host path's staging buffers, streams and running state, so repeated
+// calls pay no cudaMalloc / cudaFree / device-wide synchronisation (include/nwk.h: "no hidden
+// allocations per call" once the buffers have grown to the shapes in use).
 namespace {
 struct HostCtx {
   std::mutex mu;
   float* slab[2] = {nullptr, nullptr};
-  size_t slab_bytes = 0;
+  size_t slab_bytes[2] = {0, 0};
   float* query = nullptr;
   size_t query_bytes = 0;
-  void* ws = nullptr;
+  char* ws = nullptr;
   size_t ws_bytes = 0;
   float* part_d = nullptr;
+  size_t part_d_bytes = 0;
   long long* part_i = nullptr;
-  size_t part_n = 0;
+  size_t part_i_bytes = 0;
+  nwk_topk_state* state = nullptr;      // running result of multi-slab calls, reused while (nq, k) stay the same
   cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
   bool init = false;
 };
-HostCtx g_host;
+HostCtx g_host[NWK_MAX_DEVICES];
 
 template <typename T>
 int grow(T** p, size_t* have, size_t want) {
-  if (*have >= want) return NWK_OK;
+  if (*have >= want && *p) return NWK_OK;
   if (*p) cudaFree(*p);
   *p = nullptr;
   *have = 0;
   cudaError_t e = cudaMalloc(p, want);
-  if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    return fail(NWK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
   *have = want;
   return NWK_OK;
 }
@@ -153,15 +187,25 @@ static int knn_impl(const float* base, int64_t nb, const float* query, int64_t n
     return fail(NWK_ERR_WORKSPACE, "workspace of %zu bytes is smaller than nwk_knn_workspace_bytes() = %zu",
                 ws_bytes, nwk_knn_workspace_bytes(nb, nq, d, k, metric, flags));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // (the tensor-core path reads rows as 16-byte vectors and through TMA)
+  // (the tensor-core path reads rows as 16-byte vectors and through TMA; base or query pointers that
+  // are not 16-byte aligned take the fp64 scan, in rounds that fit the same workspace)
   const bool aligned = ((reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(query)) & 15u) == 0;
   if (want_tc(nb, nq, d, k, flags) && aligned)
     return tc_knn(base, nb, query, nq, d, k, metric, id_offset, out_dist, (long long*)out_idx, workspace,
                   ws_bytes, flags, stats, s, bound, bound_stride);
-  // the fp64 scan ignores the bound: it returns the slab's full top-k, a superset of what the caller needs
+  // The fp64 scan ignores the bound: it returns the slab's full top-k, a superset of what the caller
+  // needs.  The workspace may have been sized for the tensor-core path (which provisions the scan for
+  // 64 queries): the scan then walks the queries in rounds that fit, as the fallback does.
   const long long l0 = g_launches.load();
-  NWK_TRY(exact_scan(base, nb, query, d, k, metric, id_offset, nullptr, nq, out_dist, (long long*)out_idx,
-                     workspace, ws_bytes, s));
+  long long per = nq;
+  while (per > 8 && exact_scan_workspace_bytes(nb, per, k) > ws_bytes) per = (per + 1) / 2;
+  if (exact_scan_workspace_bytes(nb, per, k) > ws_bytes)
+    return fail(NWK_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one round of the exact scan", ws_bytes);
+  for (long long q0 = 0; q0 < nq; q0 += per) {
+    const long long n = std::min<long long>(per, nq - q0);
+    NWK_TRY(exact_scan(base, nb, query + (size_t)q0 * d, d, k, metric, id_offset, nullptr, n, out_dist + (size_t)q0 * k,
+                       (long long*)out_idx + (size_t)q0 * k, workspace, ws_bytes, s));
+  }
   NWK_CUDA(cudaStreamSynchronize(s));
   if (stats) {
     stats->path = 0;
@@ -182,22 +226,46 @@ size_t nwk_merge_workspace_bytes(int32_t P, int64_t nq, int32_t k_in, int32_t k_
   return merge_workspace_bytes(P, nq, k_in, k_out);
 }
 
-int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq, int32_t k_in, int32_t k_out,
-                   float* out_dist, int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream) {
+static int merge_args_check(int32_t P, const void* dist, const void* idx, int64_t nq, int32_t k_in, int32_t k_out,
+                            const void* out_dist, const void* out_idx) {
   if (!dist || !idx || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
   if (P <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(NWK_ERR_ARG, "bad merge shape");
-  if (k_out > NWK_MAX_K) return fail(NWK_ERR_ARG, "k_out=%d exceeds %d", k_out, NWK_MAX_K);
+  if (k_out > NWK_MERGE_MAX_K) return fail(NWK_ERR_ARG, "k_out=%d exceeds %d", k_out, NWK_MERGE_MAX_K);
   if ((long long)k_out > (long long)P * k_in)
     return fail(NWK_ERR_ARG, "k_out=%d exceeds the %lld candidates per query", k_out, (long long)P * k_in);
-  NWK_TRY(device_check());
+  return device_check();
+}
+
+int nwk_merge_topk(int32_t P, const float* dist, const int64_t* idx, int64_t nq, int32_t k_in, int32_t k_out,
+                   float* out_dist, int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream) {
+  NWK_TRY(merge_args_check(P, dist, idx, nq, k_in, k_out, out_dist, out_idx));
   return merge_topk(P, dist, (const long long*)idx, nq, k_in, k_out, out_dist, (long long*)out_idx, workspace,
                     ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nwk_merge_topk_strided(int32_t P, const float* dist, int64_t dist_stride, const int64_t* idx, int64_t idx_stride,
+                           int64_t nq, int32_t k_in, int32_t k_out, float* out_dist, int64_t* out_idx, void* workspace,
+                           size_t ws_bytes, void* stream) {
+  NWK_TRY(merge_args_check(P, dist, idx, nq, k_in, k_out, out_dist, out_idx));
+  return merge_topk_strided(P, dist, dist_stride, (const long long*)idx, idx_stride, nq, k_in, k_out, out_dist,
+                            (long long*)out_idx, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nwk_merge_topk_ptrs(int32_t P, const float* const* dist_ptrs, const int64_t* const* idx_ptrs, int64_t nq,
+                        int32_t k_in, int32_t k_out, float* out_dist, int64_t* out_idx, void* workspace,
+                        size_t ws_bytes, void* stream) {
+  NWK_TRY(merge_args_check(P, dist_ptrs, idx_ptrs, nq, k_in, k_out, out_dist, out_idx));
+  for (int p = 0; p < P && p < 16; ++p)
+    if (!dist_ptrs[p] || !idx_ptrs[p]) return fail(NWK_ERR_ARG, "null list pointer %d", p);
+  return merge_topk_ptrs(P, dist_ptrs, reinterpret_cast<const long long* const*>(idx_ptrs), nq, k_in, k_out, out_dist,
+                         (long long*)out_idx, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // ---- running top-k state --------------------------------------------------------------
 struct nwk_topk_state {
   long long nq;
   int k;
+  int device;
   float* pack_d;       // [2][nq][k]: slot 0 = current result, slot 1 = incoming partial
   long long* pack_i;
   float* tmp_d;        // [nq][k]
@@ -206,12 +274,20 @@ struct nwk_topk_state {
   size_t ws_bytes;
 };
 
+int nwk_topk_state_reset(nwk_topk_state* st, void* stream) {
+  if (!st) return fail(NWK_ERR_ARG, "null pointer argument");
+  state_init_kernel<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(st->pack_d, st->pack_i, (long long)st->nq * st->k);
+  NWK_LAUNCH_CHECK();
+  return NWK_OK;
+}
+
 int nwk_topk_state_create(int64_t nq, int32_t k, nwk_topk_state** out) {
   if (!out || nq <= 0 || k <= 0 || k > NWK_MAX_K) return fail(NWK_ERR_ARG, "bad topk state shape");
   NWK_TRY(device_check());
   nwk_topk_state* st = new nwk_topk_state();
   st->nq = nq;
   st->k = k;
+  cudaGetDevice(&st->device);
   const size_t n = (size_t)nq * k;
   st->ws_bytes = merge_workspace_bytes(2, nq, k, k);
   cudaError_t e = cudaSuccess;
@@ -224,10 +300,20 @@ int nwk_topk_state_create(int64_t nq, int32_t k, nwk_topk_state** out) {
     nwk_topk_state_destroy(st);
     return fail(NWK_ERR_CUDA, "topk state allocation failed: %s", cudaGetErrorString(e));
   }
-  state_init_kernel<<<256, 256>>>(st->pack_d, st->pack_i, (long long)n);
-  NWK_LAUNCH_CHECK();
-  NWK_CUDA(cudaDeviceSynchronize());
+  // (the legacy default stream orders this initialisation before any later work of blocking streams;
+  //  callers on non-blocking streams are covered by the synchronisation)
+  int rc = nwk_topk_state_reset(st, nullptr);
+  if (rc == NWK_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = fail(NWK_ERR_CUDA, "topk state initialisation failed");
+  if (rc != NWK_OK) { nwk_topk_state_destroy(st); return rc; }
   *out = st;
+  return NWK_OK;
+}
+
+// the running result moves from tmp back into slot 0 (two device copies, enqueued)
+static int state_commit(nwk_topk_state* st, cudaStream_t s) {
+  const size_t n = (size_t)st->nq * st->k;
+  NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
   return NWK_OK;
 }
 
@@ -238,9 +324,7 @@ int nwk_topk_state_update(nwk_topk_state* st, const float* dist, const int64_t* 
   NWK_CUDA(cudaMemcpyAsync(st->pack_d + n, dist, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   NWK_CUDA(cudaMemcpyAsync(st->pack_i + n, idx, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
   NWK_TRY(merge_topk(2, st->pack_d, st->pack_i, st->nq, st->k, st->k, st->tmp_d, st->tmp_i, st->ws, st->ws_bytes, s));
-  NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
-  return NWK_OK;
+  return state_commit(st, s);
 }
 
 int nwk_topk_state_search(nwk_topk_state* st, const float* base, int64_t nb, const float* query, int32_t d,
@@ -253,17 +337,16 @@ int nwk_topk_state_search(nwk_topk_state* st, const float* base, int64_t nb, con
   NWK_TRY(knn_impl(base, nb, query, st->nq, d, st->k, metric, id_offset, st->pack_d + n, (int64_t*)(st->pack_i + n),
                    workspace, ws_bytes, flags, stats, stream, st->pack_d + (st->k - 1), st->k));
   NWK_TRY(merge_topk(2, st->pack_d, st->pack_i, st->nq, st->k, st->k, st->tmp_d, st->tmp_i, st->ws, st->ws_bytes, s));
-  NWK_CUDA(cudaMemcpyAsync(st->pack_d, st->tmp_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  NWK_CUDA(cudaMemcpyAsync(st->pack_i, st->tmp_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
-  return NWK_OK;
+  return state_commit(st, s);
 }
 
 int nwk_topk_state_finalize(nwk_topk_state* st, float* out_dist, int64_t* out_idx, void* stream) {
   if (!st || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = (size_t)st->nq * st->k;
-  NWK_CUDA(cudaMemcpyAsync(out_dist, st->pack_d, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  NWK_CUDA(cudaMemcpyAsync(out_idx, st->pack_i, n * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  // (cudaMemcpyDefault: the destination may be device memory or pinned / pageable host memory)
+  NWK_CUDA(cudaMemcpyAsync(out_dist, st->pack_d, n * sizeof(float), cudaMemcpyDefault, s));
+  NWK_CUDA(cudaMemcpyAsync(out_idx, st->pack_i, n * sizeof(long long), cudaMemcpyDefault, s));
   return NWK_OK;
 }
 
@@ -280,28 +363,20 @@ int nwk_topk_state_destroy(nwk_topk_state* st) {
 
 // ---- host-buffer path -----------------------------------------------------------------
 
-int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host, int64_t nq, int32_t d,
-                     int32_t k, int32_t metric, int64_t id_offset, int64_t slab_rows, float* out_dist_host,
-                     int64_t* out_idx_host, uint32_t flags, nwk_knn_stats* stats) {
-  if (!base_host || !query_host || !out_dist_host || !out_idx_host) return fail(NWK_ERR_ARG, "null pointer argument");
-  if (nb <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > NWK_MAX_K || k > nb) return fail(NWK_ERR_ARG, "bad shape");
-  NWK_TRY(device_check());
-  std::lock_guard<std::mutex> lock(g_host.mu);
-  HostCtx& c = g_host;
-  if (!c.init) {
-    NWK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-    NWK_CUDA(cudaStreamCreateWithFlags(&c.comp_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      NWK_CUDA(cudaEventCreateWithFlags(&c.copied[i], cudaEventDisableTiming));
-      NWK_CUDA(cudaEventCreateWithFlags(&c.freed[i], cudaEventDisableTiming));
-    }
-    c.init = true;
-  }
+// Slab partition of nwk_knn_host_f32: slabs 0 .. nslab-2 hold slab_rows rows, the last one the
+// remainder.  Every slab must hold at least k rows (the reference asserts the same of its last
+// batch, cu_knn.py:177): a tail shorter than k is folded into the slab before it, so the last
+// slab -- and the device ring -- holds fewer than slab_rows + k rows.
+int nwk_host_slab_plan(int64_t nb, int64_t nq, int32_t d, int32_t k, int64_t slab_rows_in, int64_t* slab_rows_out,
+                       int64_t* nslab_out, int64_t* last_rows_out) {
+  if (nb <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > nb || !slab_rows_out || !nslab_out || !last_rows_out)
+    return fail(NWK_ERR_ARG, "bad slab plan arguments");
+  long long slab_rows = slab_rows_in;
   if (slab_rows <= 0) {
-    // 8 slabs so the first copy is a small part of the run, but slabs of at least 64K rows so the
-    // per-slab fixed cost stays negligible.  That fixed cost is per QUERY (a sample pass and a
+    // Default: 8 slabs so the first copy is a small part of the run, but slabs of at least 64K rows so
+    // the per-slab fixed cost stays negligible.  That fixed cost is per QUERY (a sample pass and a
     // finish stage per slab: 10-20 ms per slab at 100 000 queries, against 10 ms of exposed first
-    // copy per GB), so large query sets take fewer, larger slabs.
+    // copy per GB), so large query sets take fewer, larger slabs; a slab is at most 6 GB.
     const long long want = nq > 50000 ? 3 : (nq > 20000 ? 4 : 8);
     slab_rows = (nb + want - 1) / want;
     if (slab_rows < 65536) slab_rows = 65536;
@@ -311,44 +386,72 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
   if (slab_rows > nb) slab_rows = nb;
   if (slab_rows < k) slab_rows = k;
   long long nslab = (nb + slab_rows - 1) / slab_rows;
-  // the last slab must still hold k rows (the reference asserts the same of its last
-  // batch, cu_knn.py:177): fold a short tail into the previous slab
-  if (nslab > 1 && nb - (nslab - 1) * slab_rows < k) {
+  long long last = nb - (nslab - 1) * slab_rows;
+  if (nslab > 1 && last < k) {
     nslab -= 1;
-    slab_rows = (nb + nslab - 1) / nslab;
+    last += slab_rows;
   }
+  *slab_rows_out = slab_rows;
+  *nslab_out = nslab;
+  *last_rows_out = last;
+  return NWK_OK;
+}
+
+int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host, int64_t nq, int32_t d,
+                     int32_t k, int32_t metric, int64_t id_offset, int64_t slab_rows_arg, float* out_dist_host,
+                     int64_t* out_idx_host, uint32_t flags, nwk_knn_stats* stats) {
+  if (!base_host || !query_host || !out_dist_host || !out_idx_host) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (nb <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > NWK_MAX_K || k > nb) return fail(NWK_ERR_ARG, "bad shape");
+  if (metric < 0 || metric > 2) return fail(NWK_ERR_ARG, "unknown metric %d", metric);
+  NWK_TRY(device_check());
+  int dev = 0;
+  cudaGetDevice(&dev);
+  HostCtx& c = g_host[dev];
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!c.init) {
+    NWK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    NWK_CUDA(cudaStreamCreateWithFlags(&c.comp_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      NWK_CUDA(cudaEventCreateWithFlags(&c.copied[i], cudaEventDisableTiming));
+      NWK_CUDA(cudaEventCreateWithFlags(&c.freed[i], cudaEventDisableTiming));
+    }
+    c.init = true;
+  }
+  int64_t slab_rows = 0, nslab = 0, last_rows = 0;
+  NWK_TRY(nwk_host_slab_plan(nb, nq, d, k, slab_rows_arg, &slab_rows, &nslab, &last_rows));
+  auto rows_of = [&](long long i) -> long long { return i + 1 < nslab ? slab_rows : last_rows; };
+  const long long ring_rows = std::max<long long>(slab_rows, last_rows);
   const size_t n_out = (size_t)nq * k;
-  size_t ws_need = 0;
-  for (long long i = 0; i < nslab; ++i) {
-    long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
-    size_t w = nwk_knn_workspace_bytes(rows, nq, d, k, metric, flags);
-    if (w > ws_need) ws_need = w;
+  size_t ws_need = nwk_knn_workspace_bytes(ring_rows, nq, d, k, metric, flags);
+  if (nslab > 1) ws_need = std::max(ws_need, nwk_knn_workspace_bytes(slab_rows, nq, d, k, metric, flags));
+  // slot of slab i: i & 1; the (longer) last slab needs ring_rows only in its own slot
+  for (int b = 0; b < 2; ++b) {
+    const bool holds_last = ((nslab - 1) & 1) == b;
+    if (b == 1 && nslab == 1) break;
+    NWK_TRY(grow(&c.slab[b], &c.slab_bytes[b], (size_t)(holds_last ? ring_rows : slab_rows) * d * 4));
   }
-  size_t sb = c.slab_bytes;
-  NWK_TRY(grow(&c.slab[0], &sb, (size_t)slab_rows * d * 4));
-  sb = c.slab_bytes;
-  NWK_TRY(grow(&c.slab[1], &sb, (size_t)slab_rows * d * 4));
-  c.slab_bytes = sb;
   NWK_TRY(grow(&c.query, &c.query_bytes, (size_t)nq * d * 4));
-  NWK_TRY(grow(reinterpret_cast<char**>(&c.ws), &c.ws_bytes, ws_need));
-  if (c.part_n < n_out) {
-    if (c.part_d) cudaFree(c.part_d);
-    if (c.part_i) cudaFree(c.part_i);
-    c.part_d = nullptr; c.part_i = nullptr; c.part_n = 0;
-    NWK_CUDA(cudaMalloc(&c.part_d, n_out * sizeof(float)));
-    NWK_CUDA(cudaMalloc(&c.part_i, n_out * sizeof(long long)));
-    c.part_n = n_out;
-  }
+  NWK_TRY(grow(&c.ws, &c.ws_bytes, ws_need));
   nwk_topk_state* st = nullptr;
-  if (nslab > 1) NWK_TRY(nwk_topk_state_create(nq, k, &st));
+  if (nslab > 1) {
+    if (c.state && (c.state->nq != nq || c.state->k != k)) {
+      nwk_topk_state_destroy(c.state);
+      c.state = nullptr;
+    }
+    if (!c.state) NWK_TRY(nwk_topk_state_create(nq, k, &c.state));
+    st = c.state;
+    NWK_TRY(nwk_topk_state_reset(st, c.comp_stream));
+  } else {
+    NWK_TRY(grow(&c.part_d, &c.part_d_bytes, n_out * sizeof(float)));
+    NWK_TRY(grow(&c.part_i, &c.part_i_bytes, n_out * sizeof(long long)));
+  }
 
   nwk_knn_stats total{};
   int rc = NWK_OK;
   auto enqueue_copy = [&](long long i) -> int {
     const int b = (int)(i & 1);
-    long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
     NWK_CUDA(cudaStreamWaitEvent(c.copy_stream, c.freed[b], 0));
-    NWK_CUDA(cudaMemcpyAsync(c.slab[b], base_host + (size_t)i * slab_rows * d, (size_t)rows * d * 4,
+    NWK_CUDA(cudaMemcpyAsync(c.slab[b], base_host + (size_t)i * slab_rows * d, (size_t)rows_of(i) * d * 4,
                              cudaMemcpyHostToDevice, c.copy_stream));
     NWK_CUDA(cudaEventRecord(c.copied[b], c.copy_stream));
     return NWK_OK;
@@ -364,16 +467,15 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
     if ((rc = enqueue_copy(0)) != NWK_OK) break;
     for (long long i = 0; i < nslab && rc == NWK_OK; ++i) {
       const int b = (int)(i & 1);
-      long long rows = std::min<long long>(slab_rows, nb - i * slab_rows);
       if (i + 1 < nslab && (rc = enqueue_copy(i + 1)) != NWK_OK) break;   // overlaps with this slab's search
       rc = [&]() -> int {
         NWK_CUDA(cudaStreamWaitEvent(c.comp_stream, c.copied[b], 0));
         nwk_knn_stats s1{};
         if (st)
-          NWK_TRY(nwk_topk_state_search(st, c.slab[b], rows, c.query, d, metric, id_offset + i * slab_rows, c.ws,
+          NWK_TRY(nwk_topk_state_search(st, c.slab[b], rows_of(i), c.query, d, metric, id_offset + i * slab_rows, c.ws,
                                         c.ws_bytes, flags, &s1, c.comp_stream));
         else
-          NWK_TRY(nwk_knn_f32(c.slab[b], rows, c.query, nq, d, k, metric, id_offset + i * slab_rows, c.part_d,
+          NWK_TRY(nwk_knn_f32(c.slab[b], rows_of(i), c.query, nq, d, k, metric, id_offset + i * slab_rows, c.part_d,
                               (int64_t*)c.part_i, c.ws, c.ws_bytes, flags, &s1, c.comp_stream));
         NWK_CUDA(cudaEventRecord(c.freed[b], c.comp_stream));
         total.path = s1.path;
@@ -401,9 +503,26 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
     cudaStreamSynchronize(c.copy_stream);
     cudaStreamSynchronize(c.comp_stream);
   }
-  if (st) nwk_topk_state_destroy(st);
   if (stats && rc == NWK_OK) *stats = total;
   return rc;
+}
+
+// Frees what the host path has cached on the current device (staging ring, workspace, running state).
+int nwk_host_release(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= NWK_MAX_DEVICES) return NWK_OK;
+  HostCtx& c = g_host[dev];
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int b = 0; b < 2; ++b) { if (c.slab[b]) cudaFree(c.slab[b]); c.slab[b] = nullptr; c.slab_bytes[b] = 0; }
+  if (c.query) cudaFree(c.query);
+  if (c.ws) cudaFree(c.ws);
+  if (c.part_d) cudaFree(c.part_d);
+  if (c.part_i) cudaFree(c.part_i);
+  c.query = nullptr; c.ws = nullptr; c.part_d = nullptr; c.part_i = nullptr;
+  c.query_bytes = c.ws_bytes = c.part_d_bytes = c.part_i_bytes = 0;
+  if (c.state) nwk_topk_state_destroy(c.state);
+  c.state = nullptr;
+  return NWK_OK;
 }
 
 size_t nwk_maxsim_workspace_bytes(int64_t nq, int32_t tq, int64_t nd, int32_t td, int32_t d, int32_t k) {

@@ -62,7 +62,25 @@ struct Arena {
   bool ok() const { return off <= size; }
 };
 
-int device_check();  // verifies an sm_100 device is current; caches the answer
+// Per-device state.  Function attributes (dynamic shared-memory opt-ins), the SM count and
+// the library's own streams are properties of ONE device, so everything the library caches
+// is keyed by the ordinal of the device that is current when an entry point is called: a
+// process may drive several GPUs (one host thread per device, nwk_mg_*) or one (the
+// one-process-per-GPU model of the Python drivers).
+constexpr int NWK_MAX_DEVICES = 64;
+constexpr int NWK_SIDE_STREAMS = 2;
+struct DevState {
+  int checked = 0;              // 1 once the device was verified to be sm_100
+  int sms = 0;
+  int tc_optin = 0, seg_optin = 0, scan_optin = 0, ms_optin = 0;
+  int rr_optin = 48 * 1024, merge_rank_optin = 48 * 1024, ms_ex_optin = 48 * 1024;
+  // fork / join inside one call (nwk_tc.cu): side streams and the events that order them
+  cudaStream_t side[NWK_SIDE_STREAMS] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NWK_SIDE_STREAMS] = {nullptr, nullptr};
+  cudaEvent_t ev_chunk[16] = {};
+};
+int device_check();             // verifies that the current device is sm_100; caches the answer per device
+DevState* dev_state();          // state of the current device (device_check() has succeeded on it)
 int sm_count();
 
 // ---------------------------------------------------------------------------------------

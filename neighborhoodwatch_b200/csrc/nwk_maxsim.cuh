@@ -587,10 +587,9 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   p.nQT = pl.nQT; p.G = pl.G; p.nUnits = pl.nUnits; p.sc = sc; p.neg_score = neg; p.err = &sc->err;
   {
     const int smem = STAGES * STAGE_BYTES + 256 + 1024;
-    static bool optin = false;
-    if (!optin) {
+    if (!dev_state()->ms_optin) {
       NWK_CUDA(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      optin = true;
+      dev_state()->ms_optin = 1;
     }
     maxsim_kernel<<<pl.nUnits < sms ? pl.nUnits : sms, MS_THREADS, smem, s>>>(tm_q, tm_d, p);
     NWK_LAUNCH_CHECK();
@@ -603,10 +602,9 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   int tj = (64 * 1024 / (d * 8)) / 8 * 8;
   tj = tj < 8 ? 8 : (tj > 64 ? 64 : tj);
   const int ex_smem = tj * d * 8 + 8 * Tq * 8 + 64;
-  static int ex_optin = 48 * 1024;
-  if (ex_smem > ex_optin) {
+  if (ex_smem > dev_state()->ms_ex_optin) {
     NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
-    ex_optin = ex_smem;
+    dev_state()->ms_ex_optin = ex_smem;
   }
   const float c_rel = (float)(1.0 / 1024.0 * 1.001 + ((double)d / 16.0 + 2.0) / 4194304.0);
   MsExact e{};

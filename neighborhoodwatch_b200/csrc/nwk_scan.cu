@@ -121,13 +121,34 @@ scan_dist_kernel(const float* __restrict__ base, long long nb, const float* __re
 // ---------------------------------------------------------------------------------------
 enum { SRC_IOTA = 0, SRC_PAIRS = 1, SRC_MERGE = 2 };
 
+// Where the P partial lists of a merge live: list p is [nq][k_in] row-major at dist_tab[p] / idx_tab[p]
+// (P <= MERGE_TAB pointers: lists in the memory of P peer GPUs, or in separately allocated buffers), or
+// at dist + p * dist_stride / idx + p * idx_stride (any P: one contiguous [P, nq, k_in] array, or the
+// chunks of a packed all-gather buffer).
+constexpr int MERGE_TAB = 16;
+struct MergeSrc {
+  const float* dist;
+  const long long* idx;
+  long long dist_stride, idx_stride;        // elements between consecutive lists
+  int use_tab;
+  const float* dist_tab[MERGE_TAB];
+  const long long* idx_tab[MERGE_TAB];
+  __device__ __forceinline__ const float* d(int p) const { return use_tab ? dist_tab[p] : dist + p * dist_stride; }
+  __device__ __forceinline__ const long long* i(int p) const { return use_tab ? idx_tab[p] : idx + p * idx_stride; }
+};
+
+// Padding of a partial list is marked by a negative id (-1), whatever its distance: it orders after
+// every real entry -- including real entries whose distance is +inf or nan (nan sorts as +inf) -- and
+// comes out as (+inf, -1) again.
+constexpr long long PAD_ID = 0x7fffffffffffffffLL;
+
 struct SegArgs {
   const double* in_key;
   const long long* in_id;
-  const float* in_f32;      // SRC_MERGE
+  MergeSrc src;             // SRC_MERGE
+  long long q0;             // SRC_MERGE: first query of this launch
   long long n;              // elements per query
   long long in_stride;      // stride between queries (elements) for SRC_IOTA / SRC_PAIRS
-  long long nq;             // SRC_MERGE: queries (partial stride = nq * k_in)
   int k_in;                 // SRC_MERGE
   int k;
   double* out_key;
@@ -166,10 +187,11 @@ seg_topk_kernel(SegArgs a) {
         kv = a.in_key[f * a.in_stride + e];
         iv = a.in_id[f * a.in_stride + e];
       } else {
-        long long p = e / a.k_in, j = e - p * a.k_in;
-        long long off = (p * a.nq + f) * a.k_in + j;
-        kv = (double)a.in_f32[off];
-        iv = a.in_id[off];
+        const int p = (int)(e / a.k_in);
+        const long long off = (a.q0 + f) * a.k_in + (e - (long long)p * a.k_in);
+        kv = (double)a.src.d(p)[off];
+        iv = a.src.i(p)[off];
+        if (iv < 0) { kv = INF; iv = PAD_ID; }
       }
       if (kv != kv) kv = INF;   // NaN sorts last
     }
@@ -193,8 +215,8 @@ seg_topk_kernel(SegArgs a) {
 }
 
 static int seg_smem_optin() {
-  static bool done = false;
-  if (!done) {
+  DevState* ds = dev_state();
+  if (!ds->seg_optin) {
     const int bytes = SEG * 16;
     cudaError_t e;
     e = cudaFuncSetAttribute(seg_topk_kernel<SRC_IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -203,7 +225,7 @@ static int seg_smem_optin() {
     if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "smem opt-in failed: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(seg_topk_kernel<SRC_MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "smem opt-in failed: %s", cudaGetErrorString(e));
-    done = true;
+    ds->seg_optin = 1;
   }
   return NWK_OK;
 }
@@ -331,12 +353,12 @@ int exact_scan(const float* base, long long nb, const float* query, int d, int k
 
   const size_t q_smem = (size_t)SCAN_QG * d * sizeof(float);
   if (q_smem > 200 * 1024) return fail(NWK_ERR_ARG, "d=%d too large for the exact scan", d);
-  static bool optin = false;
-  if (!optin) {
+  DevState* ds = dev_state();
+  if (!ds->scan_optin) {
     NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NWK_CUDA(cudaFuncSetAttribute(scan_dist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    optin = true;
+    ds->scan_optin = 1;
   }
   const int sms = sm_count();
   for (long long f0 = 0; f0 < nsel; f0 += fc) {
@@ -400,8 +422,8 @@ constexpr int RANK_MERGE_MAX = 2048;
 constexpr int RANK_MERGE_THREADS = 128;
 
 __global__ void __launch_bounds__(RANK_MERGE_THREADS)
-merge_rank_kernel(const float* __restrict__ dist, const long long* __restrict__ idx, int P, long long nq, int k_in,
-                  int k_out, float* __restrict__ out_dist, long long* __restrict__ out_idx) {
+merge_rank_kernel(const MergeSrc src, int P, long long nq, int k_in, int k_out, float* __restrict__ out_dist,
+                  long long* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char rm_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = P * k_in;
@@ -413,22 +435,23 @@ merge_rank_kernel(const float* __restrict__ dist, const long long* __restrict__ 
   bool sorted = true;
   for (int e = lane; e < n; e += 32) {
     const int b = e / k_in, j = e - b * k_in;
-    const size_t g = ((size_t)b * nq + q) * k_in + j;
-    float d = dist[g];
+    const size_t g = (size_t)q * k_in + j;
+    float d = src.d(b)[g];
+    long long id = src.i(b)[g];
     if (!(d == d)) d = INF;
+    if (id < 0) { d = INF; id = PAD_ID; }           // padding: after every real entry
     s_d[e] = d;
-    s_id[e] = idx[g];
+    s_id[e] = id;
   }
-  for (int j = lane; j < k_out; j += 32) { out_dist[q * k_out + j] = INF; out_idx[q * k_out + j] = -1; }
   __syncwarp();
   for (int e = lane; e < n; e += 32)
     if ((e % k_in) != 0 && s_d[e - 1] > s_d[e]) sorted = false;
   sorted = __all_sync(0xffffffffu, sorted);
+  // (distance, id, position) is a strict total order over the n entries, so the ranks are a
+  // permutation of 0 .. n-1 and every output slot below min(k_out, n) has exactly one writer
   for (int e = lane; e < n; e += 32) {
     const float d = s_d[e];
-    if (!(d < INF)) continue;                       // padding
     const long long id = s_id[e];
-    const int a = e / k_in;
     int rank = 0;
     if (sorted) {
       for (int b = 0; b < P; ++b) {
@@ -452,22 +475,21 @@ merge_rank_kernel(const float* __restrict__ dist, const long long* __restrict__ 
         if (fd < d || (fd == d && (fid < id || (fid == id && f < e)))) ++rank;
       }
     }
-    (void)a;
-    if (rank < k_out) { out_dist[q * k_out + rank] = d; out_idx[q * k_out + rank] = id; }
+    if (rank < k_out) { out_dist[q * k_out + rank] = d; out_idx[q * k_out + rank] = (id == PAD_ID) ? -1 : id; }
   }
 }
 
-static int merge_rank(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
-                      float* out_dist, long long* out_idx, cudaStream_t s) {
+static int merge_rank(const MergeSrc& src, int P, long long nq, int k_in, int k_out, float* out_dist, long long* out_idx,
+                      cudaStream_t s) {
   const int n = P * k_in;
   const int smem = (RANK_MERGE_THREADS / 32) * n * 12;
-  static int optin = 48 * 1024;
-  if (smem > optin) {
+  DevState* ds = dev_state();
+  if (smem > ds->merge_rank_optin) {
     NWK_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    optin = smem;
+    ds->merge_rank_optin = smem;
   }
   const long long blocks = (nq + RANK_MERGE_THREADS / 32 - 1) / (RANK_MERGE_THREADS / 32);
-  merge_rank_kernel<<<(unsigned)blocks, RANK_MERGE_THREADS, smem, s>>>(dist, idx, P, nq, k_in, k_out, out_dist, out_idx);
+  merge_rank_kernel<<<(unsigned)blocks, RANK_MERGE_THREADS, smem, s>>>(src, P, nq, k_in, k_out, out_dist, out_idx);
   NWK_LAUNCH_CHECK();
   return NWK_OK;
 }
@@ -479,13 +501,15 @@ size_t merge_workspace_bytes(int P, long long nq, int k_in, int k_out) {
   return 2 * (align_up((size_t)nq * nseg * k_out * 8, 256) * 2) + 4096;
 }
 
-int merge_topk(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
-               float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+int merge_topk_src(const MergeSrc& src, int P, long long nq, int k_in, int k_out, float* out_dist, long long* out_idx,
+                   void* ws, size_t ws_bytes, cudaStream_t s) {
   if (nq == 0) return NWK_OK;
   if (ws_bytes < merge_workspace_bytes(P, nq, k_in, k_out))
     return fail(NWK_ERR_WORKSPACE, "merge workspace too small");
   if ((long long)P * k_in <= RANK_MERGE_MAX && nq < (1ll << 31) * (RANK_MERGE_THREADS / 32))
-    return merge_rank(P, dist, idx, nq, k_in, k_out, out_dist, out_idx, s);
+    return merge_rank(src, P, nq, k_in, k_out, out_dist, out_idx, s);
+  // segmented path: every round keeps k_out of each 4096-record segment, so k_out <= SEG / 2 converges
+  if (k_out > SEG / 2) return fail(NWK_ERR_ARG, "k_out=%d exceeds %d", k_out, SEG / 2);
   long long n = (long long)P * k_in;
   long long nseg = (n + SEG - 1) / SEG;
   Arena ar(ws, ws_bytes);
@@ -502,10 +526,9 @@ int merge_topk(int P, const float* dist, const long long* idx, long long nq, int
   for (long long q0 = 0; q0 < nq; q0 += SLICE) {
     long long nf = min(SLICE, nq - q0);
     SegArgs a{};
-    a.in_f32 = dist + q0 * k_in;
-    a.in_id = idx + q0 * k_in;
+    a.src = src;
+    a.q0 = q0;
     a.n = n;
-    a.nq = nq;
     a.k_in = k_in;
     a.k = k_out;
     a.out_dist = out_dist + q0 * k_out;
@@ -514,6 +537,29 @@ int merge_topk(int P, const float* dist, const long long* idx, long long nq, int
     NWK_TRY(run_topk_rounds<SRC_MERGE>(a, (int)nf, ping_k, ping_i, pong_k, pong_i, s));
   }
   return NWK_OK;
+}
+
+int merge_topk_strided(int P, const float* dist, long long dist_stride, const long long* idx, long long idx_stride,
+                       long long nq, int k_in, int k_out, float* out_dist, long long* out_idx, void* ws,
+                       size_t ws_bytes, cudaStream_t s) {
+  MergeSrc src{};
+  src.dist = dist; src.idx = idx; src.dist_stride = dist_stride; src.idx_stride = idx_stride; src.use_tab = 0;
+  return merge_topk_src(src, P, nq, k_in, k_out, out_dist, out_idx, ws, ws_bytes, s);
+}
+
+int merge_topk_ptrs(int P, const float* const* dist, const long long* const* idx, long long nq, int k_in, int k_out,
+                    float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (P > MERGE_TAB) return fail(NWK_ERR_ARG, "at most %d separately placed lists per merge", MERGE_TAB);
+  MergeSrc src{};
+  src.use_tab = 1;
+  for (int p = 0; p < P; ++p) { src.dist_tab[p] = dist[p]; src.idx_tab[p] = idx[p]; }
+  return merge_topk_src(src, P, nq, k_in, k_out, out_dist, out_idx, ws, ws_bytes, s);
+}
+
+int merge_topk(int P, const float* dist, const long long* idx, long long nq, int k_in, int k_out,
+               float* out_dist, long long* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  return merge_topk_strided(P, dist, nq * (long long)k_in, idx, nq * (long long)k_in, nq, k_in, k_out, out_dist,
+                            out_idx, ws, ws_bytes, s);
 }
 
 // ---------------------------------------------------------------------------------------

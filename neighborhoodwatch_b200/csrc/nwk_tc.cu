@@ -1599,8 +1599,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
 }
 
 static int tc_optin() {
-  static bool done = false;
-  if (!done) {
+  DevState* ds = dev_state();          // cudaFuncSetAttribute is per device
+  if (!ds->tc_optin) {
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -1612,7 +1612,7 @@ static int tc_optin() {
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_SAMPLE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_FILTER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     NWK_CUDA(cudaFuncSetAttribute(tc_kernel<MODE_DUMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    done = true;
+    ds->tc_optin = 1;
   }
   return NWK_OK;
 }
@@ -1917,10 +1917,10 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     select_kernel<<<(unsigned)((nq + SEL_THREADS / 32 - 1) / (SEL_THREADS / 32)), SEL_THREADS, 0, s>>>(f);
     NWK_LAUNCH_CHECK();
     const int rr_smem = (d + 3) / 4 * 16;
-    static int rr_optin = 48 * 1024;
-    if (rr_smem > rr_optin) {
+    DevState* ds = dev_state();
+    if (rr_smem > ds->rr_optin) {
       NWK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rr_smem));
-      rr_optin = rr_smem;
+      ds->rr_optin = rr_smem;
     }
     // a query's batches are dealt over grid.y CTAs; every warp prefetches one batch ahead
     // (measured best split: 1 at d = 128, 4 at d = 768, 8 at d = 1536 -- longer rows want more

@@ -11,6 +11,7 @@ order).  The exchange is 12*Q*k bytes per rank (12 MB at Q=10^4, k=100).
 """
 from __future__ import annotations
 
+import inspect
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -26,7 +27,8 @@ def shard_bounds(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]
 
 
 def gather_partials(local_d: torch.Tensor, local_i: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather ``[Q, k]`` partials into ``[W, Q, k]`` (the only collective on the path)."""
+    """All-gather ``[Q, k]`` partials into ``[W, Q, k]`` as two collectives (kept for callers that hold
+    separate tensors; ``sharded_knn`` uses the packed single-collective exchange below)."""
     world = dist.get_world_size(group)
     local_d = local_d.contiguous()
     local_i = local_i.contiguous()
@@ -39,34 +41,89 @@ def gather_partials(local_d: torch.Tensor, local_i: torch.Tensor, group=None) ->
     return all_d.view(world, nq, k), all_i.view(world, nq, k)
 
 
+# ---- packed exchange: ONE collective moves distances and ids together -------------------------
+# chunk of a rank = [Q*k f32 | pad to 16 B | Q*k i64] (knn.packed_chunk_bytes); the local top-k is
+# written straight into the send chunk by the kernel (no packing pass), the gathered buffer is merged
+# in place by nwk_merge_topk_strided (no unpacking pass).
+_xbuf: dict = {}
+last_exchange: Optional[str] = None      # which exchange served the last sharded call (diagnostics / tests)
+
+
+def _chunk_bytes(nq: int, k: int) -> int:
+    return (nq * k * 4 + 15) // 16 * 16 + nq * k * 8
+
+
+def _chunk_views(buf: torch.Tensor, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    off = (nq * k * 4 + 15) // 16 * 16
+    return (buf[: nq * k * 4].view(torch.float32).view(nq, k), buf[off: off + nq * k * 8].view(torch.int64).view(nq, k))
+
+
+def exchange_buffers(nq: int, k: int, world: int, device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(send chunk, gather buffer of ``world`` chunks), cached per shape and device."""
+    key = (nq, k, world, device.type, device.index)
+    bufs = _xbuf.get(key)
+    if bufs is None:
+        _xbuf.clear()                                  # one shape at a time: keeps HBM for the base
+        chunk = _chunk_bytes(nq, k)
+        bufs = (torch.empty(chunk, dtype=torch.uint8, device=device),
+                torch.empty(world * chunk, dtype=torch.uint8, device=device))
+        _xbuf[key] = bufs
+    return bufs
+
+
 def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric: str, row_offset: int,
                 group=None, local_knn: Optional[Callable] = None, merge: Optional[Callable] = None
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exact global top-k when every rank holds ``local_base`` = its shard of the base rows.
 
-    ``local_knn`` / ``merge`` default to the libnwk kernels; the gloo CPU tests inject array
-    stand-ins so the sharding / offset / gather logic is exercised without a GPU.
-    Shards smaller than k contribute all their rows, padded with +inf / -1.
+    ``local_knn(base, queries, k, metric, offset, out=None)`` / ``merge(all_d, all_i, k)`` default to
+    the libnwk kernels; the gloo CPU tests inject array stand-ins so the sharding / offset / packing /
+    gather logic is exercised without a GPU.  Shards smaller than k contribute all their rows, padded
+    with +inf / -1.
     """
-    if local_knn is None or merge is None:
+    global last_exchange
+    nq = queries.shape[0]
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    native = local_knn is None
+    if native:
         from . import knn as _knn
-        local_knn = local_knn or (lambda b, q, kk, m, off: _knn.knn(b, q, kk, metric=m, id_offset=off))
-        merge = merge or _knn.merge_topk
+
+        def local_knn(b, q, kk, m, off, out=None):
+            return _knn.knn(b, q, kk, metric=m, id_offset=off, out=out)
     kk = min(k, local_base.shape[0])
-    if kk > 0:
-        d_loc, i_loc = local_knn(local_base, queries, kk, metric, row_offset)
+    if world == 1:
+        if kk == k:
+            return local_knn(local_base, queries, k, metric, row_offset)
+        sbuf = torch.empty(_chunk_bytes(nq, k), dtype=torch.uint8, device=queries.device)
     else:
-        d_loc = torch.empty((queries.shape[0], 0), dtype=torch.float32, device=queries.device)
-        i_loc = torch.empty((queries.shape[0], 0), dtype=torch.int64, device=queries.device)
-    if kk < k:
-        pad_d = torch.full((queries.shape[0], k - kk), float("inf"), dtype=d_loc.dtype, device=d_loc.device)
-        pad_i = torch.full((queries.shape[0], k - kk), -1, dtype=i_loc.dtype, device=i_loc.device)
-        d_loc = torch.cat([d_loc, pad_d], dim=1)
-        i_loc = torch.cat([i_loc, pad_i], dim=1)
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        sbuf, gbuf = exchange_buffers(nq, k, world, queries.device)
+    d_loc, i_loc = _chunk_views(sbuf, nq, k)
+    if kk == k:
+        # the kernel writes its [Q, k] lists straight into the send chunk
+        if "out" in inspect.signature(local_knn).parameters:
+            out = local_knn(local_base, queries, k, metric, row_offset, out=(d_loc, i_loc))
+        else:                                          # injected stand-in without an ``out`` parameter
+            out = local_knn(local_base, queries, k, metric, row_offset)
+        if out[0].data_ptr() != d_loc.data_ptr():
+            d_loc.copy_(out[0])
+            i_loc.copy_(out[1])
+    else:
+        d_loc.fill_(float("inf"))
+        i_loc.fill_(-1)
+        if kk > 0:
+            dd, ii = local_knn(local_base, queries, kk, metric, row_offset)
+            d_loc[:, :kk] = dd
+            i_loc[:, :kk] = ii
+    if world == 1:
         return d_loc, i_loc
-    all_d, all_i = gather_partials(d_loc, i_loc, group)
-    return merge(all_d, all_i, k)
+    dist.all_gather_into_tensor(gbuf, sbuf, group=group)
+    last_exchange = "packed-all-gather"
+    if merge is None:
+        from . import knn as _knn
+        return _knn.merge_topk_packed(gbuf, world, nq, k, k)
+    chunk = _chunk_bytes(nq, k)
+    views = [_chunk_views(gbuf[p * chunk:(p + 1) * chunk], nq, k) for p in range(world)]
+    return merge(torch.stack([v[0] for v in views]), torch.stack([v[1] for v in views]), k)
 
 
 def sharded_maxsim(query_tokens: torch.Tensor, local_doc_tokens: torch.Tensor, k: int, doc_offset: int,

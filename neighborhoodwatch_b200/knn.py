@@ -105,6 +105,11 @@ def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Ten
     dist = dist.to(torch.float32).contiguous()
     idx = idx.to(torch.int64).contiguous()
     P, nq, k_in = dist.shape
+    if k > _native.MERGE_MAX_K:
+        # the reference merge (merge.py:73-104) takes any k; the device merge keeps k records of every
+        # 4096-record segment per round and needs k <= 2048 to converge
+        raise ValueError(f"merge_topk supports k <= {_native.MERGE_MAX_K}, got {k}")
+    assert k <= P * k_in, f"k={k} exceeds the {P * k_in} candidates per query"
     dev = dist.device
     with torch.cuda.device(dev):
         out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -115,6 +120,38 @@ def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Ten
         ws = _workspace(ws_bytes, dev)
         rc = lib.nwk_merge_topk(P, dist.data_ptr(), idx.data_ptr(), nq, k_in, k, out_d.data_ptr(),
                                 out_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _native.check(rc)
+    return out_d, out_i
+
+
+def packed_chunk_bytes(nq: int, k: int) -> int:
+    """Bytes of one rank's chunk of a packed exchange buffer: ``[nq*k f32 | pad to 16 B | nq*k i64]``."""
+    return (nq * k * 4 + 15) // 16 * 16 + nq * k * 8
+
+
+def packed_views(buf: torch.Tensor, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(distances f32 [nq,k], indices i64 [nq,k]) views into one chunk (a uint8 tensor)."""
+    off = (nq * k * 4 + 15) // 16 * 16
+    return (buf[: nq * k * 4].view(torch.float32).view(nq, k), buf[off: off + nq * k * 8].view(torch.int64).view(nq, k))
+
+
+def merge_topk_packed(buf: torch.Tensor, parts: int, nq: int, k_in: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge the ``parts`` chunks of a packed exchange buffer (``nwk_merge_topk_strided``): what one
+    all-gather of ``packed_chunk_bytes`` per rank delivers, merged without unpacking."""
+    lib = _native.load()
+    assert buf.device.type == "cuda" and buf.dtype == torch.uint8 and buf.is_contiguous()
+    chunk = packed_chunk_bytes(nq, k_in)
+    assert buf.numel() == parts * chunk
+    if k > _native.MERGE_MAX_K:
+        raise ValueError(f"merge_topk supports k <= {_native.MERGE_MAX_K}, got {k}")
+    dev = buf.device
+    off = (nq * k_in * 4 + 15) // 16 * 16
+    with torch.cuda.device(dev):
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        ws = _workspace(lib.nwk_merge_workspace_bytes(parts, nq, k_in, k), dev)
+        rc = lib.nwk_merge_topk_strided(parts, buf.data_ptr(), chunk // 4, buf.data_ptr() + off, chunk // 8, nq, k_in, k,
+                                        out_d.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         _native.check(rc)
     return out_d, out_i
 
@@ -167,6 +204,11 @@ class RunningTopK:
             _native.check(self._lib.nwk_topk_state_finalize(self._handle, out_d.data_ptr(), out_i.data_ptr(),
                                                             _stream_ptr(self.device)))
         return out_d, out_i
+
+    def reset(self) -> None:
+        """Empty the state (enqueued on the current stream) so the handle serves another run."""
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.nwk_topk_state_reset(self._handle, _stream_ptr(self.device)))
 
     def close(self) -> None:
         if self._handle:

@@ -260,12 +260,12 @@ def compare_knn(got_d: np.ndarray, got_i: np.ndarray, dataset: np.ndarray, queri
     mism = np.argwhere(got_i != truth_i)
     tie_swaps = 0
     if mism.size:
-        b64 = np.asarray(dataset, dtype=np.float64)
         q64 = np.asarray(queries, dtype=np.float64)
         for r, c in mism:
             j = int(got_i[r, c]) - id_offset
-            assert 0 <= j < len(b64), f"index out of range at {(r, c)}: {got_i[r, c]}"
-            dj = distances_f64(b64[j:j + 1], q64[r:r + 1], metric)[0, 0]
+            assert 0 <= j < len(dataset), f"index out of range at {(r, c)}: {got_i[r, c]}"
+            # (only the rows in question are widened: the dataset may be a multi-GB shard)
+            dj = distances_f64(np.asarray(dataset[j:j + 1], dtype=np.float64), q64[r:r + 1], metric)[0, 0]
             ref = truth_d64[r, c]
             tie_tol = tie_rtol * max(abs(ref), abs(dj)) + atol * 1e-1
             assert abs(dj - ref) <= tie_tol, (

@@ -58,3 +58,35 @@ def test_workspace_query_is_pure():
     b = lib.nwk_knn_workspace_bytes(10 ** 6, 10 ** 4, 768, 100, 1, 0)
     assert a == b and a > 10 ** 4 * 4096 * 8
     assert lib.nwk_merge_workspace_bytes(8, 10 ** 4, 100, 100) >= 256
+
+
+def _slab_plan(lib, nb, nq, d, k, slab_rows):
+    from ctypes import byref, c_int64
+    sr, ns, last = c_int64(), c_int64(), c_int64()
+    rc = lib.nwk_host_slab_plan(nb, nq, d, k, slab_rows, byref(sr), byref(ns), byref(last))
+    return rc, sr.value, ns.value, last.value
+
+
+def test_host_slab_plan_every_slab_holds_k_rows():
+    """nb=206,k=51,slab_rows=15 and nb=1005,k=10,slab_rows=10 used to give a short (or
+    negative) last slab.  Fuzz (nb, k, slab_rows): the slabs tile [0, nb) exactly, each holds >= k rows,
+    and the device ring (the longest slab) stays below slab_rows + k."""
+    import random
+    lib = _native.load()
+    cases = [(206, 51, 15), (1005, 10, 10), (1000, 100, 100), (100, 100, 7), (101, 100, 100), (10 ** 6, 100, 0)]
+    rnd = random.Random(7)
+    for _ in range(20000):
+        nb = rnd.randint(1, 5000)
+        k = rnd.randint(1, min(nb, 300))
+        cases.append((nb, k, rnd.choice([0, rnd.randint(1, 2 * nb), rnd.randint(1, 64)])))
+    for nb, k, slab_rows in cases:
+        rc, sr, ns, last = _slab_plan(lib, nb, 7, 8, k, slab_rows)
+        assert rc == 0, (nb, k, slab_rows)
+        assert ns >= 1 and sr >= k and last >= k, (nb, k, slab_rows, sr, ns, last)
+        assert (ns - 1) * sr + last == nb, (nb, k, slab_rows, sr, ns, last)
+        assert last < sr + k, (nb, k, slab_rows, sr, ns, last)
+        if slab_rows >= k:
+            assert sr == min(slab_rows, nb)
+    # bad arguments are refused, not planned
+    assert _slab_plan(lib, 10, 1, 8, 11, 0)[0] == 1
+    assert _slab_plan(lib, 0, 1, 8, 1, 0)[0] == 1
