@@ -220,6 +220,12 @@ int nwk_maxsim_f32(const float* query_tokens, int64_t nq, int32_t tq, const floa
 int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t row0,
                    int32_t normalize, void* stream);
 
+/* Column-per-dimension staging -> the row-major array knn() takes: src is [d, ld] fp32 (element
+ * (row r, dimension c) at src[c * ld + r], the layout of the reference's parquet files,
+ * generate_dataset.py:233-235), dst is [rows, d] row-major.  Replaces cupy.copy(order='C') at
+ * cu_knn.py:211,235 / cu_knn_ds.py:197,211.  Device pointers, enqueued on `stream`. */
+int nwk_rows_from_columns_f32(const float* src, int64_t ld, int32_t d, int64_t rows, float* dst, void* stream);
+
 /* Post-validator with the reference's acceptance rule (parquet_to_format.py:351-383): for every
  * query q and returned neighbour j, numpy.isclose(1 - dot(query_q, base[idx[q,j]]), dist[q,j] / 2)
  * (squared L2 on unit vectors; the reference's defaults are rtol = 1e-5, atol = 1e-8); zero query

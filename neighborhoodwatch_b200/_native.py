@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "nwk_topk_state_search", "nwk_topk_state_finalize", "nwk_topk_state_destroy", "nwk_knn_host_f32", "nwk_synth_fill",
     "nwk_debug_tc_tile", "nwk_validate_pairs", "nwk_maxsim_workspace_bytes", "nwk_maxsim_f32",
     "nwk_merge_topk_strided", "nwk_merge_topk_ptrs", "nwk_topk_state_reset", "nwk_host_slab_plan", "nwk_host_release",
+    "nwk_rows_from_columns_f32",
 )
 
 
@@ -95,6 +96,8 @@ def load() -> ctypes.CDLL:
     lib.nwk_host_slab_plan.restype = c_int32
     lib.nwk_host_slab_plan.argtypes = [c_int64, c_int64, c_int32, c_int32, c_int64, POINTER(c_int64), POINTER(c_int64),
                                        POINTER(c_int64)]
+    lib.nwk_rows_from_columns_f32.restype = c_int32
+    lib.nwk_rows_from_columns_f32.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p]
     lib.nwk_host_release.restype = c_int32
     lib.nwk_host_release.argtypes = []
     lib.nwk_topk_state_create.restype = c_int32

@@ -36,6 +36,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
                 int k, long long id_offset, float* out_score, long long* out_idx, void* ws, size_t ws_bytes,
                 nwk_knn_stats* stats, cudaStream_t s);
 
+int rows_from_columns(const float* src, long long ld, int d, long long rows, float* dst, cudaStream_t s);
 int validate_pairs(const float* base, long long nb, const float* query, long long nq, int d, const long long* idx,
                    const float* dist, int k, double rtol, double atol, long long* out_host, cudaStream_t s);
 
@@ -546,6 +547,12 @@ int nwk_synth_fill(float* out, int64_t rows, int32_t d, uint64_t seed, int64_t r
   if (!out || rows < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad synth arguments");
   NWK_TRY(device_check());
   return synth_fill(out, rows, d, seed, row0, normalize, static_cast<cudaStream_t>(stream));
+}
+
+int nwk_rows_from_columns_f32(const float* src, int64_t ld, int32_t d, int64_t rows, float* dst, void* stream) {
+  if (!src || !dst || d <= 0 || rows < 0 || ld < rows) return fail(NWK_ERR_ARG, "bad layout arguments");
+  NWK_TRY(device_check());
+  return rows_from_columns(src, ld, d, rows, dst, static_cast<cudaStream_t>(stream));
 }
 
 int nwk_validate_pairs(const float* base, int64_t nb, const float* query, int64_t nq, int32_t d, const int64_t* idx,

@@ -12,6 +12,11 @@ re-uploads all queries per batch (cu_knn_ds.py:206-211) and mis-offsets short re
 pinned host slabs and copied on a side stream while the previous slab is searched, every
 slab's exact top-k is folded into a running device-side state (``nwk_topk_state``), offsets
 are the true global row numbers, and the final files are written once.
+
+Multi-GPU (one process per GPU, ``torch.distributed`` initialised by the launcher): rank r streams
+only rows ``shard_bounds(base_count, W, r)`` of the base dataset (row groups before its range are
+skipped without being read), keeps its own running top-k, and ONE packed all-gather + merge kernel
+at the end produce the global result; rank 0 writes the final files.
 """
 from __future__ import annotations
 
@@ -23,8 +28,11 @@ import pyarrow as pa
 import pyarrow.dataset as ds
 import torch
 
+import math
+
 from . import knn as _knn
-from .cu_knn import _device, cleanup, stream_cudf_to_parquet, tune_memory as _tune_table  # noqa: F401
+from .cu_knn import (_device, _world, cleanup, plan_batch_size, stream_cudf_to_parquet,  # noqa: F401
+                     tune_memory as _tune_table)
 from .nw_utils import (ensure_partial_dir, get_full_filename, get_partial_distances_filename,
                        get_partial_indices_filename)
 
@@ -79,30 +87,61 @@ def tune_memory(dataset, batch_size, max_memory_threshold, rmm=None, column_name
         return int(0.8 * batch_size)
 
 
-def _iter_slabs(dataset, columns: List[str], limit: int, slab_rows: int) -> Iterator[Tuple[int, int, List[pa.RecordBatch]]]:
-    """Yield (global_row_offset, rows, record batches) covering exactly ``slab_rows`` rows
-    each (the last one shorter), for the first ``limit`` rows of the dataset."""
+def _iter_record_batches(dataset, columns: List[str], start: int, stop: int, batch_rows: int) -> Iterator[pa.RecordBatch]:
+    """Record batches covering rows ``[start, stop)`` of the dataset, in order.  Row groups that lie
+    wholly before ``start`` are skipped on their metadata (never decoded): a rank of a multi-GPU run
+    pays for its own shard only."""
+    pos = 0
+    for frag in dataset.get_fragments():
+        try:
+            pieces = frag.split_by_row_group()
+        except Exception:  # noqa: BLE001 -- not a parquet fragment
+            pieces = [frag]
+        for piece in pieces:
+            if pos >= stop:
+                return
+            n = piece.count_rows()
+            if pos + n <= start:
+                pos += n
+                continue
+            for batch in piece.to_batches(columns=columns, batch_size=batch_rows):
+                b0 = pos
+                pos += len(batch)
+                lo, hi = max(b0, start), min(pos, stop)
+                if hi > lo:
+                    yield batch.slice(lo - b0, hi - lo)
+                if pos >= stop:
+                    return
+
+
+def _iter_slabs(dataset, columns: List[str], limit: int, slab_rows: int, start: int = 0,
+                min_rows: int = 1) -> Iterator[Tuple[int, int, List[pa.RecordBatch]]]:
+    """Yield (global_row_offset, rows, record batches) covering rows ``[start, limit)`` of the dataset
+    in slabs of exactly ``slab_rows`` rows; a tail shorter than ``min_rows`` is folded into the slab
+    before it (so the last slab holds fewer than ``slab_rows + min_rows`` rows and, unless the whole
+    range is shorter, at least ``min_rows``: every knn() call needs k rows, cu_knn_ds.py:204)."""
+    total = max(0, limit - start)
+    nslab = max(1, -(-total // slab_rows))
+    if nslab > 1 and total - (nslab - 1) * slab_rows < min_rows:
+        nslab -= 1
     pending: List[pa.RecordBatch] = []
     have = 0
-    start = 0
-    seen = 0
-    for batch in dataset.to_batches(columns=columns, batch_size=min(slab_rows, 131072)):
-        if seen >= limit:
-            break
-        if seen + len(batch) > limit:
-            batch = batch.slice(0, limit - seen)
-        seen += len(batch)
+    off = start
+    idx = 0
+    for batch in _iter_record_batches(dataset, columns, start, limit, min(slab_rows, 131072)):
         while len(batch):
-            take = min(len(batch), slab_rows - have)
+            want = slab_rows if idx < nslab - 1 else total - (nslab - 1) * slab_rows
+            take = min(len(batch), want - have)
             pending.append(batch.slice(0, take))
             have += take
             batch = batch.slice(take)
-            if have == slab_rows:
-                yield start, have, pending
-                start += have
+            if have == want:
+                yield off, have, pending
+                off += have
+                idx += 1
                 pending, have = [], 0
     if have:
-        yield start, have, pending
+        yield off, have, pending
 
 
 def _fill_pinned(staging: np.ndarray, batches: List[pa.RecordBatch], columns: List[str]) -> None:
@@ -141,7 +180,11 @@ def compute_knn_ds(data_dir,
     query_count = min(query_count, dataset_count(query_dataset))
 
     if mem_tune:
-        batch_size = tune_memory(base_dataset, batch_size, max_memory_threshold, None, base_column_names)
+        # planned, not searched (the reference's trial loop is cu_knn_ds.py:57-105): a slab and its
+        # double-buffer twin beside the engine's workspace, within max_memory_threshold of the device
+        rank, world = _world()
+        batch_size = plan_batch_size(math.ceil(base_count / world), dimensions, query_count, k,
+                                     max_memory_threshold / 2)
     batch_size = int(min(batch_size, base_count))
 
     # cu_knn_ds.py:168
@@ -163,29 +206,35 @@ def process_dataset_batches(data_dir,
                             split,
                             base_count=None,
                             device=None):
-    """cu_knn_ds.py:181-239 with a running global top-k and a double-buffered loader."""
+    """cu_knn_ds.py:181-239 with a running global top-k, a double-buffered loader and rank sharding."""
+    from . import dist as _dist
     device = device or _device()
-    ensure_partial_dir(data_dir)
+    rank, world = _world()
+    if rank == 0:
+        ensure_partial_dir(data_dir)
     if base_count is None:
         base_count = dataset_count(base_dataset)
     d = len(base_column_names)
+    shard_lo, shard_hi = _dist.shard_bounds(base_count, world, rank)
+    shard_rows = shard_hi - shard_lo
 
     # queries: resident for the whole run
     q_table = query_dataset.head(query_count, columns=query_column_names)
     q_stage = torch.empty((d, len(q_table)), dtype=torch.float32, pin_memory=True)
     _fill_pinned(q_stage.numpy(), q_table.to_batches(), query_column_names)
-    queries = q_stage.to(device).t().contiguous()
+    queries = _knn.rows_from_columns(q_stage.to(device))
     nq = queries.shape[0]
     assert nq == query_count                                        # cu_knn_ds.py:229-230
 
+    ring_rows = int(min(batch_size + k, max(shard_rows, 1)))        # a folded tail adds fewer than k rows
     copy_stream = torch.cuda.Stream(device=device)
-    staging = [torch.empty((d, batch_size), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    staging = [torch.empty((d, ring_rows), dtype=torch.float32, pin_memory=True) for _ in range(2)]
     staged_evt = [torch.cuda.Event() for _ in range(2)]
-    dev_cm = [torch.empty((d, batch_size), dtype=torch.float32, device=device) for _ in range(2)]
-    state = _knn.RunningTopK(nq, k, device) if base_count > batch_size else None
-    result = None
+    dev_cm = [torch.empty((d, ring_rows), dtype=torch.float32, device=device) for _ in range(2)]
+    dev_rm = torch.empty((ring_rows, d), dtype=torch.float32, device=device)
+    state = _knn.RunningTopK(nq, k, device)
 
-    slabs = _iter_slabs(base_dataset, base_column_names, base_count, batch_size)
+    slabs = _iter_slabs(base_dataset, base_column_names, shard_hi, batch_size, start=shard_lo, min_rows=k)
     # a reader thread decodes parquet into the pinned slab while the GPU works
     lock = threading.Semaphore(2)
     ready: list = []
@@ -227,24 +276,33 @@ def process_dataset_batches(data_dir,
             i, offset, rows = ready.pop(0)
         b = i & 1
         main_stream.wait_event(staged_evt[b])
-        dataset = dev_cm[b][:, :rows].t().contiguous()
+        dataset = _knn.rows_from_columns(dev_cm[b], rows, out=dev_rm)      # [d, rows] -> [rows, d], our kernel
         if split:
-            assert (k <= len(dataset))                              # cu_knn_ds.py:204
-        if state is not None:
+            assert (k <= rows) or rows == shard_rows                # cu_knn_ds.py:204 (a whole shard may be short)
+        if rows >= k:
             # knn of this slab folded into the running result; the current k-th distances bound the search
             state.search(dataset, queries, metric="sqeuclidean", id_offset=offset)
         else:
-            result = _knn.knn(dataset, queries, k, metric="sqeuclidean", id_offset=offset)
+            dd, ii = _knn.knn(dataset, queries, rows, metric="sqeuclidean", id_offset=offset)
+            pad_d = torch.full((nq, k), float("inf"), dtype=torch.float32, device=device)
+            pad_i = torch.full((nq, k), -1, dtype=torch.int64, device=device)
+            pad_d[:, :rows] = dd
+            pad_i[:, :rows] = ii
+            state.update(pad_d, pad_i)
         lock.release()
     th.join()
     if error:
         raise error[0]
-    if state is not None:
-        result = state.result()
-        torch.cuda.current_stream(device).synchronize()
-        state.close()
-    distances, indices = result
+    distances, indices = state.result()
+    torch.cuda.current_stream(device).synchronize()
+    state.close()
+    # every rank holds the exact top-k of its shard with global ids: one exchange, one merge
+    distances, indices = _dist.merge_across_ranks(distances, indices, k)
     assert (len(distances) == query_count)                          # cu_knn_ds.py:229
     assert (len(indices) == query_count)                            # cu_knn_ds.py:230
-    stream_cudf_to_parquet(get_partial_distances_filename(data_dir, -1), distances, 100000)
-    stream_cudf_to_parquet(get_partial_indices_filename(data_dir, -1), indices, 100000)
+    if rank == 0:
+        stream_cudf_to_parquet(get_partial_distances_filename(data_dir, -1), distances, 100000)
+        stream_cudf_to_parquet(get_partial_indices_filename(data_dir, -1), indices, 100000)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()

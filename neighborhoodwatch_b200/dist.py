@@ -81,7 +81,6 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
     gather logic is exercised without a GPU.  Shards smaller than k contribute all their rows, padded
     with +inf / -1.
     """
-    global last_exchange
     nq = queries.shape[0]
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     native = local_knn is None
@@ -116,6 +115,11 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
             i_loc[:, :kk] = ii
     if world == 1:
         return d_loc, i_loc
+    return _exchange_and_merge(sbuf, gbuf, nq, k, world, group, merge)
+
+
+def _exchange_and_merge(sbuf, gbuf, nq, k, world, group, merge):
+    global last_exchange
     dist.all_gather_into_tensor(gbuf, sbuf, group=group)
     last_exchange = "packed-all-gather"
     if merge is None:
@@ -124,6 +128,22 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
     chunk = _chunk_bytes(nq, k)
     views = [_chunk_views(gbuf[p * chunk:(p + 1) * chunk], nq, k) for p in range(world)]
     return merge(torch.stack([v[0] for v in views]), torch.stack([v[1] for v in views]), k)
+
+
+def merge_across_ranks(local_d: torch.Tensor, local_i: torch.Tensor, k: int, group=None,
+                       merge: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-k from every rank's finished ``[Q, k]`` list (ids already global; lists shorter than k
+    padded with +inf / -1 by the caller): the reducer the streaming driver runs once at the end."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_d, local_i
+    nq = local_d.shape[0]
+    assert local_d.shape == (nq, k) and local_i.shape == (nq, k)
+    sbuf, gbuf = exchange_buffers(nq, k, world, local_d.device)
+    d_loc, i_loc = _chunk_views(sbuf, nq, k)
+    d_loc.copy_(local_d)
+    i_loc.copy_(local_i)
+    return _exchange_and_merge(sbuf, gbuf, nq, k, world, group, merge)
 
 
 def sharded_maxsim(query_tokens: torch.Tensor, local_doc_tokens: torch.Tensor, k: int, doc_offset: int,

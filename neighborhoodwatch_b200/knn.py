@@ -93,6 +93,28 @@ def knn(dataset: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "sqe
     return out_d, out_i
 
 
+def rows_from_columns(cols: torch.Tensor, rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``[d, ld]`` column-per-dimension staging (the parquet layout) -> row-major ``[rows, d]`` by our
+    tiled transpose (``nwk_rows_from_columns_f32``; the reference: ``cupy.copy(order='C')``, cu_knn.py:211).
+    ``out``: optional ``[>= rows, d]`` buffer whose first ``rows`` rows are returned."""
+    lib = _native.load()
+    if cols.device.type != "cuda":
+        raise RuntimeError("rows_from_columns needs a CUDA tensor; this engine has no CPU path")
+    assert cols.dim() == 2 and cols.dtype == torch.float32 and cols.stride(1) == 1
+    d, ld = cols.shape[0], cols.stride(0)
+    assert d == 1 or ld >= cols.shape[1]
+    rows = cols.shape[1] if rows is None else int(rows)
+    assert rows <= cols.shape[1]
+    dev = cols.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((rows, d), dtype=torch.float32, device=dev)
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[1] == d and out.shape[0] >= rows
+        if rows:
+            _native.check(lib.nwk_rows_from_columns_f32(cols.data_ptr(), max(ld, rows), d, rows, out.data_ptr(), _stream_ptr(dev)))
+    return out[:rows]
+
+
 def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Merge ``[P, nq, k_in]`` sorted partial lists into ``[nq, k]`` by (distance, index).
 
@@ -223,7 +245,7 @@ class RunningTopK:
 
 
 def knn_host(base, queries, k: int, metric: str = "sqeuclidean", id_offset: int = 0, slab_rows: int = 0,
-             out=None):
+             out=None, force_exact_scan: bool = False):
     """Host-buffer entry point (nwk_knn_host_f32): numpy / pinned-torch arrays in, numpy out.
 
     The base is streamed through a two-deep device ring on a side stream while the previous
@@ -256,7 +278,8 @@ def knn_host(base, queries, k: int, metric: str = "sqeuclidean", id_offset: int 
         assert out_i.shape == (nq, k) and out_i.dtype == np.int64 and out_i.flags.c_contiguous
     stats = _native.KnnStats()
     rc = lib.nwk_knn_host_f32(bp[0], nb, qp[0], nq, d, k, _native.METRIC_IDS[metric], int(id_offset),
-                              int(slab_rows), out_d.ctypes.data, out_i.ctypes.data, 0, ctypes.byref(stats))
+                              int(slab_rows), out_d.ctypes.data, out_i.ctypes.data,
+                              _native.FLAG_FORCE_EXACT_SCAN if force_exact_scan else 0, ctypes.byref(stats))
     _native.check(rc)
     last_stats = stats.as_dict()
     return out_d, out_i

@@ -189,3 +189,64 @@ def test_sharded_knn_nccl_world2(tmp_path, metric, nb, d, k):
     sel = np.arange(0, nq, 5)
     res = _check(g0["d"][sel], g0["i"][sel], base, q[sel], k, metric)
     print(res, str(g0["exchange"]))
+
+
+def _write_vectors(path, vecs, row_group_size=257):
+    cols = {"document_id_idx": pa.array(np.arange(len(vecs), dtype=np.int64)), "text": pa.array(["t"] * len(vecs))}
+    for j in range(vecs.shape[1]):
+        cols[f"embedding_{j}"] = pa.array(vecs[:, j])
+    pq.write_table(pa.table(cols), path, row_group_size=row_group_size)
+
+
+def _entry_worker(rank, world, port, data_dir, nq, nb, d, k):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from neighborhoodwatch_b200 import cu_knn, cu_knn_ds, merge
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        # table API: 4 base batches, each row-sharded over the two ranks; rank 0 writes the partial files
+        cu_knn.compute_knn(os.path.join(data_dir, "a"), "intfloat/e5-small-v2", d, "query.parquet", nq, "base.parquet", nb,
+                           k=k, initial_batch_size=1000, split=True)
+        if rank == 0:
+            merge.merge_indices_and_distances(os.path.join(data_dir, "a"), k)
+        # streaming API: every rank streams its own half of the base in slabs of 400 rows
+        cu_knn_ds.compute_knn_ds(os.path.join(data_dir, "b"), d, "query.parquet", nq, "base.parquet", nb, k=k,
+                                 initial_batch_size=400)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_entry_points_are_rank_aware_world2(tmp_path):
+    """compute_knn / compute_knn_ds under a two-rank NCCL process group write the files a single-GPU
+    run writes: partial files per base batch (then merged) and the streamed final files, both equal to
+    the oracle over the whole base."""
+    import torch
+    import torch.multiprocessing as mp
+    from neighborhoodwatch_b200.nw_utils import get_partial_distances_filename, get_partial_indices_filename
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nq, nb, d, k = 150, 3010, 96, 10
+    base, q = synth.vectors(nb, d, 1234), synth.vectors(nq, d, 5678)
+    for sub in ("a", "b"):
+        os.makedirs(tmp_path / sub)
+        _write_vectors(str(tmp_path / sub / "base.parquet"), base)
+        _write_vectors(str(tmp_path / sub / "query.parquet"), q)
+    mp.spawn(_entry_worker, args=(2, _free_port(), str(tmp_path), nq, nb, d, k), nprocs=2, join=True)
+    t_d, t_i = ko.knn_f64(base, q, k, "sqeuclidean")
+
+    def read(path, dtype):
+        t = pq.read_table(path)
+        return np.stack([t.column(j).to_numpy() for j in range(t.num_columns)], axis=1).astype(dtype, copy=False)
+    partials = ko.process_batches_oracle(base, q, 4, 1000, k, True, engine="raft")
+    for i in range(4):
+        np.testing.assert_array_equal(read(get_partial_indices_filename(str(tmp_path / "a"), i), np.int64), partials[i][1])
+    for sub in ("a", "b"):
+        f_d = read(get_partial_distances_filename(str(tmp_path / sub), -1), np.float32)
+        f_i = read(get_partial_indices_filename(str(tmp_path / sub), -1), np.int64)
+        np.testing.assert_array_equal(f_i, t_i, err_msg=sub)
+        np.testing.assert_allclose(f_d, t_d, rtol=1e-5, atol=1e-6, err_msg=sub)

@@ -107,6 +107,80 @@ def test_iter_slabs_exact_offsets(tmp_path):
     assert seen == [(0, 300), (300, 300), (600, 300), (900, 50)]
 
 
+def test_iter_slabs_rank_shard_and_folded_tail(tmp_path):
+    """A rank's shard [start, limit) in slabs; a tail shorter than min_rows joins the slab before it;
+    row groups before the shard are skipped."""
+    vec = synth.vectors(1000, 4, 1)
+    pq.write_table(pa.table({f"embedding_{i}": pa.array(vec[:, i]) for i in range(4)}),
+                   str(tmp_path / "b.parquet"), row_group_size=97)
+    dset = ds.dataset(str(tmp_path / "b.parquet"), format="parquet")
+    cols = [f"embedding_{i}" for i in range(4)]
+
+    def collect(limit, slab, start, min_rows):
+        seen = []
+        for off, rows, batches in cu_knn_ds._iter_slabs(dset, cols, limit, slab, start=start, min_rows=min_rows):
+            stage = np.empty((4, rows), dtype=np.float32)
+            cu_knn_ds._fill_pinned(stage, batches, cols)
+            np.testing.assert_array_equal(stage.T, vec[off:off + rows])
+            seen.append((off, rows))
+        return seen
+    assert collect(1000, 300, 500, 1) == [(500, 300), (800, 200)]
+    assert collect(950, 300, 333, 1) == [(333, 300), (633, 300), (933, 17)]
+    assert collect(950, 300, 333, 100) == [(333, 300), (633, 317)]                # 17-row tail folded
+    assert collect(420, 300, 400, 100) == [(400, 20)]                             # a whole shard may be short
+    assert collect(500, 300, 500, 1) == []
+    # every (world, rank) split of a base tiles it exactly
+    for world in (2, 3, 8):
+        covered = []
+        for r in range(world):
+            lo, hi = nwdist.shard_bounds(987, world, r)
+            covered += collect(hi, 50, lo, 10)
+        assert covered[0][0] == 0 and sum(n for _, n in covered) == 987
+        assert all(covered[i][0] + covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+        assert all(n >= 10 for _, n in covered)
+
+
+def test_parquet_rows_reads_only_what_a_slice_needs(tmp_path):
+    vec = synth.vectors(1000, 6, 3)
+    cols = {"text": pa.array(["a"] * 1000)}
+    cols.update({f"embedding_{i}": pa.array(vec[:, i]) for i in range(6)})
+    pq.write_table(pa.table(cols), str(tmp_path / "b.parquet"), row_group_size=128)
+    names = [f"embedding_{i}" for i in range(6)]
+    rows = cu_knn.ParquetRows(str(tmp_path / "b.parquet"), names, 900)
+    assert len(rows) == 900 and rows.schema.names == names
+    for off, n in [(0, 900), (0, 1), (127, 2), (128, 128), (500, 10 ** 6), (899, 1), (900, 5)]:
+        t = rows.slice(off, n)
+        want = vec[off:min(900, off + n)]
+        assert t.schema.names == names and t.num_rows == len(want)
+        got = np.stack([t.column(j).to_numpy() for j in range(6)], axis=1) if len(want) else want
+        np.testing.assert_array_equal(got, want)
+
+
+def test_plan_batch_size():
+    """The planner that replaces tune_memory's trial loop: the reference's threshold criterion and the
+    engine's real footprint, per GPU."""
+    total = 180 << 30
+    # 10M x 1536 base, 10k queries: 10 % of 180 GB = 19.3 GB of fp32 rows = 3.1M rows (the threshold binds)
+    rows = cu_knn.plan_batch_size(10 ** 7, 1536, 10 ** 4, 100, 0.1, free_bytes=total, total_bytes=total)
+    assert rows == int(0.1 * total) // (4 * 1536)
+    # a generous threshold: the whole base in one batch when rows + workspace fit
+    assert cu_knn.plan_batch_size(10 ** 7, 1536, 10 ** 4, 100, 0.9, free_bytes=total, total_bytes=total) == 10 ** 7
+    # little free memory: the footprint binds, and what is planned does fit
+    from neighborhoodwatch_b200 import _native
+    lib = _native.load()
+    free = 8 << 30
+    rows = cu_knn.plan_batch_size(10 ** 7, 1536, 10 ** 4, 100, 0.9, free_bytes=free, total_bytes=total)
+    need = lambda r: r * 4 * 1536 + lib.nwk_knn_workspace_bytes(r, 10 ** 4, 1536, 100, 0, 0)   # noqa: E731
+    assert need(rows) <= 0.9 * free < need(rows + 1000)
+    # eight ranks share a batch: eight times the rows
+    one = cu_knn.plan_batch_size(10 ** 8, 1024, 10 ** 5, 100, 0.1, free_bytes=total, total_bytes=total)
+    eight = cu_knn.plan_batch_size(10 ** 8, 1024, 10 ** 5, 100, 0.1, world=8, free_bytes=total, total_bytes=total)
+    assert eight == 8 * one
+    # never below k, never above the table
+    assert cu_knn.plan_batch_size(50, 8, 5, 10, 0.1, free_bytes=total, total_bytes=total) == 50
+    assert cu_knn.plan_batch_size(10 ** 6, 8, 5, 100, 1e-9, free_bytes=total, total_bytes=total) == 100
+
+
 def test_merge_file_count(tmp_path):
     p = tmp_path / "partial"
     p.mkdir()
