@@ -348,7 +348,10 @@ class ShardedRun:
             pairs_ev = [ev for ev in self.exch if len(ev) == 2]
             if pairs_ev:
                 exchange_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs_ev)
+        from neighborhoodwatch_b200 import dist as nwdist
         return {"out": out, "elapsed_s": float(ms.item()) / 1e3, "launches": int(lt.item()), "clocks": clocks,
+                "exchange": (nwdist.last_exchange if self.distributed else None) if not nwdist._peer_failed
+                else f"{nwdist.last_exchange} (peer memory unavailable: {nwdist._peer_failed})",
                 "exchange_ms": exchange_ms, "local_ms_max": float(lmax.item()), "local_ms_min": float(lmin.item()),
                 "stage_ms_mean": {n: (statistics.mean(v) if v else None) for n, v in self.stage_ms.items()},
                 "agg": dict(self.agg)}
@@ -505,7 +508,7 @@ def run_config3(torch, dev, n_gpus, rank, distributed, peaks, steps=5, warmup=3)
             "aggregate_tflops": tf, "frac_of_n_x_burst": tf / (n_gpus * peaks["bf16_burst"]),
             "frac_of_n_x_sustained": tf / (n_gpus * peaks["bf16_sustained"]),
             "filter_ms": filt, "filter_tflops_per_gpu": 2.0 * nq * (hi - lo) * d / (filt * 1e-3) / 1e12 if filt else None,
-            "exchange_ms": r["exchange_ms"], "local_ms_max_over_ranks": r["local_ms_max"],
+            "exchange_ms": r["exchange_ms"], "exchange": r.get("exchange"), "local_ms_max_over_ranks": r["local_ms_max"],
             "local_ms_min_over_ranks": r["local_ms_min"], "stage_ms_mean": r["stage_ms_mean"],
             "gpu_launches": r["launches"], "fallback_queries_per_step": r["agg"]["fallback"] / steps,
             "sampled_queries_equal_fp64_scan": same}
@@ -538,7 +541,7 @@ def main():
     nb_total = nb_local * n_gpus
     config = {"workload": f"{args.workload}: {nq} queries x {nb_local} base rows per GPU x d={d}, k={k}, {metric}",
               "queries": nq, "base_rows_total": nb_total, "base_rows_per_gpu": nb_local, "d": d, "k": k,
-              "metric": metric, "sharding": f"base rows over {n_gpus} GPU(s), one packed all-gather + k-way merge kernel" if n_gpus > 1 else "single GPU",
+              "metric": metric, "sharding": f"base rows over {n_gpus} GPU(s), gather + k-way merge in one kernel over peer memory (NVLink)" if n_gpus > 1 else "single GPU",
               "l2": "inputs_exceed_l2 (base shard %.2f GB vs 126 MB L2)" % (nb_local * d * 4 / 1e9)}
 
     if args.impl == "reference":
@@ -636,7 +639,7 @@ def main():
             "clocks": r["clocks"], "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline,
             # exchange = one packed all-gather of the [Q,k] lists + the merge kernel, from the moment this rank's
             # local top-k is done (so it includes waiting for the slowest rank: the local_ms spread says how much)
-            "exchange_ms_per_step": r["exchange_ms"],
+            "exchange_ms_per_step": r["exchange_ms"], "exchange": r.get("exchange"),
             "local_knn_ms": {"max_over_ranks": r["local_ms_max"], "min_over_ranks": r["local_ms_min"]},
             "exactness": {"fallback_queries_per_step": agg["fallback"] / max(args.steps, 1),
                           "mean_candidates_per_query": agg["cand"] / max(args.steps * nq, 1),

@@ -193,6 +193,30 @@ int nwk_host_slab_plan(int64_t nb, int64_t nq, int32_t d, int32_t k, int64_t sla
  * calls (no allocation once they have grown to the shapes in use); this frees them. */
 int nwk_host_release(void);
 
+/* Cross-GPU reduction over peer memory: gather + k-way merge as ONE kernel (csrc/nwk_xchg.cu).
+ * One process per GPU on one NVLink / NVSwitch box.  Every rank creates a handle for the same
+ * (world, nq, k); the library allocates the rank's exported result buffer inside it.  The ranks
+ * swap the opaque handles of nwk_xchg_local_handle (nwk_xchg_handle_bytes() each, any transport:
+ * the Python driver uses one torch.distributed all-gather at start-up) and map them with
+ * nwk_xchg_open_peers (CUDA IPC).  Per step: write the local top-k (nwk_knn_f32 with out_dist /
+ * out_idx = the pointers of nwk_xchg_next_slot, ids global), then nwk_xchg_merge: it publishes the
+ * rank's step counter, waits -- on the device, bounded -- until every peer has published the same
+ * step, and merges the world lists of each query straight out of the owners' memory over NVLink
+ * into out_dist / out_idx [nq, k_out] (ordered by (distance, id), padding = negative ids, as
+ * nwk_merge_topk).  No collective library call and no staging copy on the step path; all ranks
+ * must call nwk_xchg_merge the same number of times.  Replaces, across GPUs, what
+ * merge_indices_and_distances (merge.py:56-101) does across the reference's base batches.
+ * nwk_xchg_check reports a timed-out wait (a rank that never published). */
+typedef struct nwk_xchg nwk_xchg;
+int nwk_xchg_create(int32_t rank, int32_t world, int64_t nq, int32_t k, nwk_xchg** out);
+size_t nwk_xchg_handle_bytes(void);
+int nwk_xchg_local_handle(nwk_xchg* x, void* handle_out);
+int nwk_xchg_open_peers(nwk_xchg* x, const void* handles);
+int nwk_xchg_next_slot(nwk_xchg* x, float** dist, int64_t** idx);
+int nwk_xchg_merge(nwk_xchg* x, int32_t k_out, float* out_dist, int64_t* out_idx, void* stream);
+int nwk_xchg_check(nwk_xchg* x);
+int nwk_xchg_destroy(nwk_xchg* x);
+
 /* Document-level ColBERT MaxSim (the reference's colbert_knn.py:62-126 stops at a
  * token-level kNN over the flattened token embeddings, which nwk_knn_f32 with NWK_METRIC_DOT covers):
  *

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnwk.so")
-SOURCES = ["nwk_api.cu", "nwk_scan.cu", "nwk_tc.cu", "nwk_synth.cu", "nwk_layout.cu"]
+SOURCES = ["nwk_api.cu", "nwk_scan.cu", "nwk_tc.cu", "nwk_synth.cu", "nwk_layout.cu", "nwk_xchg.cu"]
 HEADERS = ["nwk_common.cuh", "nwk_ptx.cuh", "nwk_maxsim.cuh", os.path.join("..", "..", "include", "nwk.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -31,7 +31,8 @@ EXPORTED_SYMBOLS = (
     "nwk_topk_state_search", "nwk_topk_state_finalize", "nwk_topk_state_destroy", "nwk_knn_host_f32", "nwk_synth_fill",
     "nwk_debug_tc_tile", "nwk_validate_pairs", "nwk_maxsim_workspace_bytes", "nwk_maxsim_f32",
     "nwk_merge_topk_strided", "nwk_merge_topk_ptrs", "nwk_topk_state_reset", "nwk_host_slab_plan", "nwk_host_release",
-    "nwk_rows_from_columns_f32",
+    "nwk_rows_from_columns_f32", "nwk_xchg_create", "nwk_xchg_handle_bytes", "nwk_xchg_local_handle",
+    "nwk_xchg_open_peers", "nwk_xchg_next_slot", "nwk_xchg_merge", "nwk_xchg_check", "nwk_xchg_destroy",
 )
 
 
@@ -98,6 +99,22 @@ def load() -> ctypes.CDLL:
                                        POINTER(c_int64)]
     lib.nwk_rows_from_columns_f32.restype = c_int32
     lib.nwk_rows_from_columns_f32.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p]
+    lib.nwk_xchg_create.restype = c_int32
+    lib.nwk_xchg_create.argtypes = [c_int32, c_int32, c_int64, c_int32, POINTER(c_void_p)]
+    lib.nwk_xchg_handle_bytes.restype = c_size_t
+    lib.nwk_xchg_handle_bytes.argtypes = []
+    lib.nwk_xchg_local_handle.restype = c_int32
+    lib.nwk_xchg_local_handle.argtypes = [c_void_p, c_void_p]
+    lib.nwk_xchg_open_peers.restype = c_int32
+    lib.nwk_xchg_open_peers.argtypes = [c_void_p, c_void_p]
+    lib.nwk_xchg_next_slot.restype = c_int32
+    lib.nwk_xchg_next_slot.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]
+    lib.nwk_xchg_merge.restype = c_int32
+    lib.nwk_xchg_merge.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.nwk_xchg_check.restype = c_int32
+    lib.nwk_xchg_check.argtypes = [c_void_p]
+    lib.nwk_xchg_destroy.restype = c_int32
+    lib.nwk_xchg_destroy.argtypes = [c_void_p]
     lib.nwk_host_release.restype = c_int32
     lib.nwk_host_release.argtypes = []
     lib.nwk_topk_state_create.restype = c_int32

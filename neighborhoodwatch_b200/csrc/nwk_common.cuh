@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/nwk.h"
@@ -78,6 +79,7 @@ struct DevState {
   cudaStream_t side[NWK_SIDE_STREAMS] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[NWK_SIDE_STREAMS] = {nullptr, nullptr};
   cudaEvent_t ev_chunk[16] = {};
+  std::recursive_mutex mu;      // one call at a time enqueues through the side streams / events of a device
 };
 int device_check();             // verifies that the current device is sm_100; caches the answer per device
 DevState* dev_state();          // state of the current device (device_check() has succeeded on it)

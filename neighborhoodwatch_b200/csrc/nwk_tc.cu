@@ -100,6 +100,8 @@ struct TcParams {
   long long nq, nb;
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
+  int t0;                   // FILTER: first base tile of this launch (the base may be filtered in parts; nT counts this part's tiles)
+  int sM;                   // SAMPLE: rank of the list entry that becomes the threshold (16 or SAMPLE_M)
   int sWarm;                // SAMPLE: 1 = start every part with the short warm-up list (large samples only)
   int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (<= SAMPLE_MAX_PARTS)
   const float* alpha;       // [nT*TB]   (SAMPLE mode: the sample rows' values, [nS*TB])
@@ -267,14 +269,22 @@ struct SampleOut {
   float* beta;              // [ns_pad]
 };
 
+// Two launch modes:
+//   rows     (so.stride_log2 < 0): rows [row_begin, row_end) of the padded base -> alpha / beta and the
+//            fp16 operand copy.  The base may be prepared in parts, on a side stream, while the filter
+//            pass already runs over the parts that are done (tc_knn).
+//   sample   (so.stride_log2 >= 0): only the stratified sample rows (one per block of 2^stride_log2
+//            rows) -> the compact sample matrix with its own alpha / beta, which the sample pass needs
+//            before any threshold exists.  Reads 1/32 .. 1/64 of the base.
 template <bool F16>
 __global__ void __launch_bounds__(256)
-baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, int d, int dh, int metric,
-                float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
+baseprep_kernel(const float* __restrict__ base, long long nb, long long row_begin, long long row_end, int d, int dh,
+                int metric, float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
                 __half* __restrict__ bh, const SampleOut so, const int direct, const int pitch) {
   // pitch = elements per row of the fp16 copies: dh, or dh + L2X_COLS for direct squared-L2 keys
   constexpr int ROW_CACHE = 8;
-  if (so.stride_log2 >= 0) {
+  const bool sample_mode = so.stride_log2 >= 0;
+  if (sample_mode) {
     const float PINF = __int_as_float(0x7f800000);
     for (long long i = so.ns + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < so.ns_pad;
          i += (long long)gridDim.x * blockDim.x) {
@@ -290,7 +300,11 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
   if (direct) direct_exps(metric, sc, sq, sbg);
   const bool l2x = direct && metric == NWK_METRIC_SQEUCLIDEAN;
   float local_max = 0.f;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < nb_pad; row += (long long)gridDim.x * 8) {
+  const long long n_items = sample_mode ? so.ns : row_end - row_begin;
+  const int wpb = blockDim.x >> 5;             // 8 warps per CTA, or 4 when the CTAs must fit beside a filter CTA
+  for (long long it = (long long)blockIdx.x * wpb + warp; it < n_items; it += (long long)gridDim.x * wpb) {
+    const long long srow = sample_mode ? it : -1;
+    const long long row = sample_mode ? sample_pick(it, so.stride_log2, nb) : row_begin + it;
     if (row >= nb) {
       if (lane == 0) { alpha[row] = INF; beta[row] = 0.f; }
       continue;
@@ -324,13 +338,7 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
     a = warp_sum(a);
     int sb = 0;
     bool row_ok = true;
-    // is this row its block's sample row?
-    long long srow = -1;
-    if (so.stride_log2 >= 0) {
-      const long long blk = row >> so.stride_log2;
-      if (sample_pick(blk, so.stride_log2, nb) == row) srow = blk;
-    }
-    if (!F16 && srow >= 0) {
+    if (!F16 && sample_mode) {
       float* frow = reinterpret_cast<float*>(so.rows) + srow * d;
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
@@ -361,8 +369,8 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         if (metric == NWK_METRIC_COSINE) scale = (float)(1.0 / sqrt(a)) * scale;   // unit row at 2^sbg
         if (!row_ok) scale = 0.f;
       }
-      __half* hrow = bh + row * pitch;
-      __half* hsrow = srow >= 0 ? reinterpret_cast<__half*>(so.rows) + srow * pitch : nullptr;
+      // the row's fp16 copy goes to the operand matrix (rows mode) or to the compact sample matrix
+      __half* hrow = sample_mode ? reinterpret_cast<__half*>(so.rows) + srow * pitch : bh + row * pitch;
       if (l2x && lane == 0) {
         // X = 2^(2s-1) |b|^2 as three fp16 pieces against the queries' 2^15, 2^4, 2^-7 (exact residuals in fp64)
         float h1 = 0.f, h2 = 0.f, h3 = 0.f;
@@ -378,7 +386,6 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         __half2 p23 = __floats2half2_rn(-h3, 0.f);
         uint4 pk4 = make_uint4(*reinterpret_cast<unsigned int*>(&p01), *reinterpret_cast<unsigned int*>(&p23), 0u, 0u);
         *reinterpret_cast<uint4*>(hrow + dh) = pk4;
-        if (hsrow) *reinterpret_cast<uint4*>(hsrow + dh) = pk4;
       }
 #pragma unroll
       for (int i = 0; i < ROW_CACHE; ++i) {
@@ -392,7 +399,6 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
           pk.y = *reinterpret_cast<unsigned int*>(&h23);
           if (!row_ok) pk = make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(hrow + c) = pk;
-          if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
         }
       }
       for (int c = lane * 4 + ROW_CACHE * 128; c < dh; c += 128) {
@@ -405,7 +411,6 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
         pk.y = *reinterpret_cast<unsigned int*>(&h23);
         if (!row_ok) pk = make_uint2(0u, 0u);
         *reinterpret_cast<uint2*>(hrow + c) = pk;
-        if (hsrow) *reinterpret_cast<uint2*>(hsrow + c) = pk;
       }
     }
     if (lane == 0) {
@@ -420,20 +425,19 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long nb_pad, 
       else if (metric == NWK_METRIC_COSINE) {
         if (a > 0.0) be = (float)(-1.0 / sqrt(a)) * unscale; else { al = INF; be = 0.f; }
       }
-      alpha[row] = al;
-      beta[row] = be;
-      if (srow >= 0) { so.alpha[srow] = al; so.beta[srow] = be; }
+      if (sample_mode) { so.alpha[srow] = al; so.beta[srow] = be; }
+      else { alpha[row] = al; beta[row] = be; }
       local_max = fmaxf(local_max, __double2float_ru(a));
     }
   }
   if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
 }
 
-// tau_q = SAMPLE_M-th smallest key of the union of the query's per-part lists (one warp per
-// query): bitwise search for the largest ordered key t with fewer than SAMPLE_M list entries
+// tau_q = m-th smallest key (m <= SAMPLE_M) of the union of the query's per-part lists (one warp per
+// query): bitwise search for the largest ordered key t with fewer than m list entries
 // below it.  Lists that were never written hold +inf.
 __global__ void __launch_bounds__(256)
-tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, float* __restrict__ tau) {
+tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, int m, float* __restrict__ tau) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * 8 + warp;
   if (q >= nq) return;
@@ -449,7 +453,7 @@ tau_merge_kernel(const float* __restrict__ slist, long long nq, int parts, float
 #pragma unroll
     for (int i = 0; i < SAMPLE_MAX_LISTS; ++i) below += (v[i] < trial) ? 1 : 0;
     below = __reduce_add_sync(0xffffffffu, below);
-    if (below < SAMPLE_M) ans = trial;
+    if (below < m) ans = trial;
   }
   if (lane == 0) tau[q] = ord2f(ans);
 }
@@ -467,12 +471,12 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 // ---------------------------------------------------------------------------------------
 template <int MODE, bool CTA2 = false>
 struct Sched {
-  int nUnits, nQT, nT, G, nS, sParts, dump_qt, dump_t;
+  int nUnits, nQT, nT, G, nS, sParts, dump_qt, dump_t, t0;
   int u, i, len, qt, c;
   int step;                 // workers walking the unit list: CTAs, or CTA pairs (both CTAs of a pair walk the same units)
   __device__ explicit Sched(const TcParams& p)
       : nUnits(p.nUnits), nQT(p.nQT), nT(p.nT), G(p.G), nS(p.nS), sParts(p.sParts), dump_qt(p.dump_qt), dump_t(p.dump_t),
-        i(0), len(0), qt(0), c(0) {
+        t0(p.t0), i(0), len(0), qt(0), c(0) {
     step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     u = (CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) - step;
   }
@@ -508,7 +512,7 @@ struct Sched {
     // (all CTAs on a chunk walk its tiles in the same order on purpose: requests for a tile that is
     //  still on its way from HBM merge in L2; rotating the order per query tile was measured:
     //  +2 % filter time at d = 768, +6 % at d = 1536)
-    if (MODE == MODE_FILTER) out_t = c * G + i;
+    if (MODE == MODE_FILTER) out_t = t0 + c * G + i;
     else if (MODE == MODE_SAMPLE) out_t = c + i;
     else out_t = dump_t;
     first = (i == 0);
@@ -814,7 +818,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           lst[0] = fminf(lst[0], key);
         }
         cnt = 0;
-        tau = fminf(tau, lst[SAMPLE_M - 1]);
+        tau = fminf(tau, p.sM <= 16 ? lst[15] : lst[SAMPLE_M - 1]);
       };
       auto chunk = [&](const uint32_t (&cur)[32], int ch) {
         if (warm < SAMPLE_WARM) {                           // warp-uniform
@@ -1623,7 +1627,7 @@ bool tc_path_supported(long long nb, long long nq, int d, int k) {
 }
 
 struct TcPlan {
-  int nQT, nT, nKB, kLast, G, nChunks, nUnits, nS, sChunks, sParts, dh, kcols, pitch;
+  int nQT, nT, nKB, kLast, G, nChunks, nUnits, nS, sChunks, sParts, dh, kcols, pitch, sM;
   bool sample;
   long long nb_pad, nq_pad;
   long long s_stride, ns, ns_pad;
@@ -1653,10 +1657,18 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
   pl.nUnits = pl.nChunks * pl.nQT;
   // sampling only pays when the base is larger than what the log can simply hold
   pl.sample = nb > LOG_CAP / 2;
+  pl.sM = SAMPLE_M;
   if (pl.sample) {
     // the SAMPLE_M-th smallest key of a sample of every `stride`-th row has about
     // SAMPLE_M * stride rows of the whole base below it
-    pl.s_stride = LOG_TARGET / SAMPLE_M;
+    // Long rows: every 64th row and the 16th smallest key (spread 1/sqrt(16) instead of 1/sqrt(32): the log
+    // holds 4 x the target): the sample pass costs 1/64 of the filter pass's FLOPs instead of 1/32.
+    // Short rows keep the denser sample: there the filter's epilogue is the limit and candidates cost more.
+    // Large query sets keep the 32-entry statistic as well: with 10^5 queries per slab the 1-in-10^5 query whose
+    // threshold comes out too low costs an fp64 scan of the slab (measured: 4 ms per 1M x 1024 slab).
+    pl.sM = (d >= 512 && nq <= 16384) ? 16 : SAMPLE_M;
+    if (const char* e = getenv("NWK_SAMPLE_M")) pl.sM = atoi(e) <= 16 ? 16 : SAMPLE_M;     // experiment switch
+    pl.s_stride = LOG_TARGET / pl.sM;
     pl.ns = (nb + pl.s_stride - 1) / pl.s_stride;
     pl.ns_pad = (pl.ns + TB - 1) / TB * TB;
     pl.nS = (int)(pl.ns_pad / TB);
@@ -1710,6 +1722,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
            long long id_offset, float* out_dist, long long* out_idx, void* ws, size_t ws_bytes,
            unsigned int flags, nwk_knn_stats* stats, cudaStream_t s, const float* bound, long long bound_stride) {
   NWK_TRY(tc_optin());
+  std::lock_guard<std::recursive_mutex> dev_lock(dev_state()->mu);
   const int sms = sm_count();
   const bool f16 = !(flags & NWK_FLAG_TF32);
   // Direct keys (no alpha / beta in the epilogue).  Cosine rows are normalised in the preparation
@@ -1777,25 +1790,81 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, pl.pitch, metric, direct ? 1 : 0, sc, qh);
     NWK_LAUNCH_CHECK();
   }
-  {
-    long long blocks = (pl.nb_pad + 7) / 8;
-    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-    SampleOut so{};
-    so.stride_log2 = -1;
-    if (pl.sample) {
-      so.stride_log2 = 0;
-      while ((1ll << so.stride_log2) < pl.s_stride) ++so.stride_log2;     // LOG_TARGET / SAMPLE_M is a power of two
-      so.ns = pl.ns; so.ns_pad = pl.ns_pad;
-      so.rows = srows; so.alpha = salpha; so.beta = sbeta;
-    }
-    if (direct && metric == NWK_METRIC_DOT) {
-      // the one extra pass the direct keys cost: the global scale needs max |b_ij| before any row is converted
-      qmax_kernel<<<sms * 8, 256, 0, s>>>(base, nb * d, &sc->babsmax);
-      NWK_LAUNCH_CHECK();
-    }
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
-    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, metric, alpha, beta, sc, bh, so, 0, pl.dh);
+  if (direct && metric == NWK_METRIC_DOT) {
+    // the one extra pass the direct keys cost: the global scale needs max |b_ij| before any row is converted
+    qmax_kernel<<<sms * 8, 256, 0, s>>>(base, nb * d, &sc->babsmax);
     NWK_LAUNCH_CHECK();
+  }
+  SampleOut no_sample{};
+  no_sample.stride_log2 = -1;
+  if (pl.sample) {
+    // the sample rows first (1/32 .. 1/64 of the base): the sample pass can start while the bulk of the
+    // base is still being prepared
+    SampleOut so{};
+    so.stride_log2 = 0;
+    while ((1ll << so.stride_log2) < pl.s_stride) ++so.stride_log2;     // a power of two (make_plan)
+    so.ns = pl.ns; so.ns_pad = pl.ns_pad;
+    so.rows = srows; so.alpha = salpha; so.beta = sbeta;
+    long long blocks = std::min<long long>((pl.ns_pad + 7) / 8, (long long)sms * 16);
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
+    else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, 0, pl.dh);
+    NWK_LAUNCH_CHECK();
+  }
+
+  // ---- the base in parts: preparation (HBM-bound) on a side stream, filter launches (tensor-bound) behind it.
+  // Part p's filter pass waits only for part p's preparation, so after the first part everything the
+  // preparation costs is hidden under the filter pass; baseprep CTAs use no shared memory and few
+  // registers, they run beside the persistent filter CTA of an SM.  A caller's distance bound
+  // (running searches) needs max |b|^2 of the whole slab before the thresholds exist: no overlap there
+  // beyond the sample pass.
+  DevState* ds = dev_state();
+  // tiles per part: multiples of the schedule's chunk of G tiles
+  const int workers = pair ? sms / 2 : sms;
+  const int nQTf = pair ? (pl.nQT + 1) / 2 : pl.nQT;          // query tiles (or tile pairs) of the filter schedule
+  int G = pl.G;
+  if (pair) {
+    long long g = (long long)nQTf * pl.nT / ((long long)workers * 8);
+    G = (int)(g < 1 ? 1 : (g > 16 ? 16 : g));
+  }
+  int nparts = 1;
+  {
+    // every part must still give each worker several units, or its tail costs more than the overlap wins
+    const long long units_total = (long long)((pl.nT + G - 1) / G) * nQTf;
+    // (the 640-thread direct-key variants leave no registers for a second CTA on their SM: no parts there)
+    const bool roomy = pair || !direct;
+    if (roomy && units_total >= (long long)workers * 24) nparts = 3;
+    else if (roomy && units_total >= (long long)workers * 12) nparts = 2;
+    if (const char* e = getenv("NWK_PARTS")) nparts = std::max(1, std::min(8, atoi(e)));     // experiment switch
+    if (nparts > (pl.nT + G - 1) / G) nparts = 1;
+  }
+  int part_t0[9];
+  {
+    const int chunks = (pl.nT + G - 1) / G;
+    // a short first part (the only preparation that is exposed), the rest evenly
+    part_t0[0] = 0;
+    for (int pi = 1; pi <= nparts; ++pi) {
+      long long c = nparts == 1 ? chunks : (long long)chunks * (2 * pi - 1) / (2 * nparts - 1);
+      if (pi == nparts) c = chunks;
+      part_t0[pi] = (int)std::min<long long>((long long)c * G, pl.nT);
+    }
+  }
+  const bool prep_aside = nparts > 1;
+  cudaStream_t sp = prep_aside ? ds->side[0] : s;
+  if (prep_aside) {
+    NWK_CUDA(cudaEventRecord(ds->ev_fork, s));
+    NWK_CUDA(cudaStreamWaitEvent(sp, ds->ev_fork, 0));
+  }
+  for (int pi = 0; pi < nparts; ++pi) {
+    const long long r0 = (long long)part_t0[pi] * TB;
+    const long long r1 = pi == nparts - 1 ? pl.nb_pad : (long long)part_t0[pi + 1] * TB;
+    // beside a 384-thread filter CTA (12 warps x 4096 registers) an SM has 16 K registers left: 4-warp
+    // CTAs of this 80-register kernel fit, 8-warp CTAs do not
+    const int threads = prep_aside ? 128 : 256;
+    long long blocks = std::min<long long>((r1 - r0) / (threads / 32) + 1, (long long)sms * (prep_aside ? 32 : 16));
+    if (f16) baseprep_kernel<true><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, direct ? 1 : 0, pl.pitch);
+    else baseprep_kernel<false><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, 0, pl.dh);
+    NWK_LAUNCH_CHECK();
+    if (prep_aside) NWK_CUDA(cudaEventRecord(ds->ev_chunk[pi], sp));
   }
   if (profile) cudaEventRecord(ev[1], s);
 
@@ -1812,7 +1881,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   p.nKB = pl.nKB; p.kLast = pl.kLast; p.nq = nq; p.nb = nb; p.nQT = pl.nQT; p.nT = pl.nT;
   p.G = pl.G; p.nChunks = pl.nChunks; p.nUnits = pl.nUnits; p.nS = pl.nS; p.sChunks = pl.sChunks; p.sParts = pl.sParts;
   p.alpha = alpha; p.beta = beta; p.tau = tau; p.slist = slist; p.cnt = cnt; p.log = log; p.err = &sc->err;
-  p.sc = sc; p.metric = metric;
+  p.sc = sc; p.metric = metric; p.sM = pl.sM;
   unsigned long long* d_prof = nullptr;
 #ifdef NWK_EXPERIMENTS
   // timing experiments (scripts/gpu_exp.sh builds libnwk_exp.so with -DNWK_EXPERIMENTS); the
@@ -1836,13 +1905,13 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     TcParams ps = p;
     ps.alpha = salpha; ps.beta = sbeta; ps.nT = pl.nS;
     // The warm-up threshold (4th smallest key of a part's first 128 sample rows) must stay above
-    // the final tau (the SAMPLE_M-th smallest of all ns rows), or list entries go missing and tau
-    // comes out too large: the chance per list is P(Poisson(128 * SAMPLE_M / ns) >= 4), 0.2 % at
-    // ns = 8192 and 1e-5 at the 31 250 rows of a 1M-row base; smaller samples insert every key.
+    // the final tau (the sM-th smallest of all ns rows), or list entries go missing and tau
+    // comes out too large: the chance per list is P(Poisson(128 * sM / ns) >= 4), 0.2 % at
+    // ns = 8192 and 1e-5 at the 31 250 rows of a 1M-row base (sM = 32); smaller samples insert every key.
     ps.sWarm = pl.ns >= 8192 ? 1 : 0;
     int grid = pl.sParts * pl.nQT < sms ? pl.sParts * pl.nQT : sms;
     NWK_TRY(f16 ? launch_tc<true>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s) : launch_tc<false>(MODE_SAMPLE, grid, tm_q, tm_s, ps, s));
-    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, pl.sParts * SAMPLE_WG, tau);
+    tau_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(slist, nq, pl.sParts * SAMPLE_WG, pl.sM, tau);
     NWK_LAUNCH_CHECK();
   } else {
     fill_f32_kernel<<<64, 256, 0, s>>>(tau, pl.nq_pad, HUGE_VALF);
@@ -1862,42 +1931,64 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   f.c_acc = (float)((steps + 1.0) / 4194304.0);
   f.out_dist = out_dist; f.out_idx = out_idx; f.fail_list = fail_list;
   if (bound) {
+    // key(D) + eps needs max |b|^2 over the whole slab
+    if (prep_aside) NWK_CUDA(cudaStreamWaitEvent(s, ds->ev_chunk[nparts - 1], 0));
     tau_bound_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(f, bound, bound_stride, tau, bflag);
     NWK_LAUNCH_CHECK();
   }
   if (profile) cudaEventRecord(ev[2], s);
-  if (pair) {
-    const int clusters = sms / 2;
+
+  // ---- filter launches: one per part, alternating between the caller's stream and a side stream.  The
+  // launches are independent of each other (log slots are reserved with atomics), so the CTAs of part
+  // p+1 move onto the SMs as the CTAs of part p leave them: no tail between the parts.
+  cudaStream_t sf = nparts > 1 ? ds->side[1] : s;
+  if (nparts > 1) {
+    NWK_CUDA(cudaEventRecord(ds->ev_fork, s));          // thresholds are ready
+    NWK_CUDA(cudaStreamWaitEvent(sf, ds->ev_fork, 0));
+  }
+  for (int pi = 0; pi < nparts; ++pi) {
+    cudaStream_t sl = (pi & 1) ? sf : s;
+    if (prep_aside) NWK_CUDA(cudaStreamWaitEvent(sl, ds->ev_chunk[pi], 0));
     TcParams pp = p;
-    pp.nQT = (pl.nQT + 1) / 2;
-    long long g = (long long)pp.nQT * pl.nT / ((long long)clusters * 8);
-    pp.G = (int)(g < 1 ? 1 : (g > 16 ? 16 : g));
-    pp.nChunks = (pl.nT + pp.G - 1) / pp.G;
+    pp.t0 = part_t0[pi];
+    pp.nT = part_t0[pi + 1] - part_t0[pi];
+    if (pp.nT <= 0) continue;
+    pp.nQT = nQTf;
+    pp.G = G;
+    pp.nChunks = (pp.nT + G - 1) / G;
     pp.nUnits = pp.nChunks * pp.nQT;
-    CUtensorMap tm_bh;
-    NWK_TRY(make_tmap(&tm_bh, bh, nb, pl.kcols, true, TB / 2, pl.pitch));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2u * (unsigned)(pp.nUnits < clusters ? pp.nUnits : clusters));
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (direct) NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true, true>, tm_q, tm_bh, pp));
-    else NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true>, tm_q, tm_bh, pp));
-    count_launch();
-  } else if (direct || ares) {
-    int grid = pl.nUnits < sms ? pl.nUnits : sms;
-    if (direct && ares) tc_kernel<MODE_FILTER, true, false, true, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    else if (direct) tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    else tc_kernel<MODE_FILTER, true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_q, tm_b, p);
-    NWK_LAUNCH_CHECK();
-  } else {
-    int grid = pl.nUnits < sms ? pl.nUnits : sms;
-    NWK_TRY(f16 ? launch_tc<true>(MODE_FILTER, grid, tm_q, tm_b, p, s) : launch_tc<false>(MODE_FILTER, grid, tm_q, tm_b, p, s));
+    if (pair) {
+      const int clusters = workers;
+      CUtensorMap tm_bh;
+      NWK_TRY(make_tmap(&tm_bh, bh, nb, pl.kcols, true, TB / 2, pl.pitch));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2u * (unsigned)(pp.nUnits < clusters ? pp.nUnits : clusters));
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+      cfg.stream = sl;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (direct) NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true, true>, tm_q, tm_bh, pp));
+      else NWK_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE_FILTER, true, true>, tm_q, tm_bh, pp));
+      count_launch();
+    } else if (direct || ares) {
+      int grid = pp.nUnits < sms ? pp.nUnits : sms;
+      if (direct && ares) tc_kernel<MODE_FILTER, true, false, true, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, sl>>>(tm_q, tm_b, pp);
+      else if (direct) tc_kernel<MODE_FILTER, true, false, true><<<grid, TC_THREADS_WIDE, TC_SMEM_BYTES, sl>>>(tm_q, tm_b, pp);
+      else tc_kernel<MODE_FILTER, true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, sl>>>(tm_q, tm_b, pp);
+      NWK_LAUNCH_CHECK();
+    } else {
+      int grid = pp.nUnits < sms ? pp.nUnits : sms;
+      NWK_TRY(f16 ? launch_tc<true>(MODE_FILTER, grid, tm_q, tm_b, pp, sl) : launch_tc<false>(MODE_FILTER, grid, tm_q, tm_b, pp, sl));
+    }
+  }
+  if (nparts > 1) {
+    // join: the finish stage needs every part's log entries
+    NWK_CUDA(cudaEventRecord(ds->ev_join[1], sf));
+    NWK_CUDA(cudaStreamWaitEvent(s, ds->ev_join[1], 0));
   }
   if (profile) cudaEventRecord(ev[3], s);
   if (d_prof) {
@@ -2022,12 +2113,12 @@ int tc_debug_tile(const float* base, long long nb, const float* query, long long
     NWK_LAUNCH_CHECK();
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, pl.dh, NWK_METRIC_DOT, 0, sc, qh);
     NWK_LAUNCH_CHECK();
-    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
+    baseprep_kernel<true><<<sms * 4, 256, 0, s>>>(base, nb, 0, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, qh, nq, pl.dh, true, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, bh, nb, pl.dh, true, TB);
   } else {
-    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
+    baseprep_kernel<false><<<sms * 4, 256, 0, s>>>(base, nb, 0, pl.nb_pad, d, pl.dh, NWK_METRIC_DOT, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     rc = make_tmap(&tm_q, query, nq, d, false, TQ);
     if (rc == NWK_OK) rc = make_tmap(&tm_b, base, nb, d, false, TB);

@@ -71,6 +71,117 @@ def exchange_buffers(nq: int, k: int, world: int, device: torch.device) -> Tuple
     return bufs
 
 
+class _DevArray:
+    """A device buffer owned by libnwk, exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerExchange:
+    """Gather + merge as one kernel over peer memory (``nwk_xchg_*``, csrc/nwk_xchg.cu).
+
+    Every rank's ``[Q, k]`` result buffer lives in memory the library exports with CUDA IPC; the merge
+    kernel of each rank reads the W lists of its queries straight from the owners' HBM over NVLink.
+    The handles are swapped once, at construction, with one torch.distributed all-gather; the step
+    path has no collective call.  ``slot()`` returns tensors over the buffer the NEXT local top-k
+    must be written to; ``merge()`` publishes it, waits (on the device) for the peers and merges."""
+
+    def __init__(self, nq: int, k: int, device: torch.device, group=None):
+        from . import _native
+        import ctypes
+        self._lib = _native.load()
+        self._native = _native
+        self.nq, self.k, self.device = nq, k, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._h = ctypes.c_void_p()
+        self._views: dict = {}
+        with torch.cuda.device(device):
+            _native.check(self._lib.nwk_xchg_create(self.rank, self.world, nq, k, ctypes.byref(self._h)))
+            hb = int(self._lib.nwk_xchg_handle_bytes())
+            mine = (ctypes.c_ubyte * hb)()
+            _native.check(self._lib.nwk_xchg_local_handle(self._h, mine))
+            send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+            recv = torch.empty(self.world * hb, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            allh = bytes(recv.cpu().numpy().tobytes())
+            rc = self._lib.nwk_xchg_open_peers(self._h, allh)
+            # every rank must agree on whether the peer path is usable
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                msg = self._lib.nwk_last_error().decode("utf-8", "replace") if rc != 0 else "a peer could not map the buffers"
+                self.close()
+                raise RuntimeError(f"peer exchange unavailable: {msg}")
+
+    def slot(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        import ctypes
+        pd, pi = ctypes.c_void_p(), ctypes.c_void_p()
+        self._native.check(self._lib.nwk_xchg_next_slot(self._h, ctypes.byref(pd), ctypes.byref(pi)))
+        views = self._views.get(pd.value)
+        if views is None:                              # two slots: two pairs of views, made once
+            views = (torch.as_tensor(_DevArray(pd.value, (self.nq, self.k), "<f4"), device=self.device),
+                     torch.as_tensor(_DevArray(pi.value, (self.nq, self.k), "<i8"), device=self.device))
+            self._views[pd.value] = views
+        return views
+
+    def merge(self, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        with torch.cuda.device(self.device):
+            out_d = torch.empty((self.nq, k_out), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((self.nq, k_out), dtype=torch.int64, device=self.device)
+            self._native.check(self._lib.nwk_xchg_merge(self._h, k_out, out_d.data_ptr(), out_i.data_ptr(),
+                                                        torch.cuda.current_stream(self.device).cuda_stream))
+        return out_d, out_i
+
+    def check(self) -> None:
+        self._native.check(self._lib.nwk_xchg_check(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._views.clear()
+            self._lib.nwk_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_peer: dict = {}
+_peer_failed: Optional[str] = None
+
+
+def peer_exchange(nq: int, k: int, device: torch.device, group=None) -> Optional[PeerExchange]:
+    """The peer-memory exchange for this shape, or None when it cannot be set up here (no CUDA IPC between
+    the ranks, more than 16 ranks, world * k > 2048): the packed all-gather serves the step then.
+    ``NWK_EXCHANGE=allgather`` forces the collective."""
+    global _peer_failed
+    import os
+    if os.environ.get("NWK_EXCHANGE", "") == "allgather" or _peer_failed is not None:
+        return None
+    if device.type != "cuda" or dist.get_backend(group) != "nccl":
+        return None
+    world = dist.get_world_size(group)
+    if world > 16 or world * k > 2048:
+        return None
+    key = (nq, k, world, device.index)
+    x = _peer.get(key)
+    if x is None:
+        for old in list(_peer.values()):
+            old.close()
+        _peer.clear()
+        try:
+            x = PeerExchange(nq, k, device, group)
+        except Exception as e:  # noqa: BLE001 -- fall back to the collective, remember why
+            _peer_failed = repr(e)[:300]
+            return None
+        _peer[key] = x
+    return x
+
+
 def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric: str, row_offset: int,
                 group=None, local_knn: Optional[Callable] = None, merge: Optional[Callable] = None
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -89,14 +200,21 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
 
         def local_knn(b, q, kk, m, off, out=None):
             return _knn.knn(b, q, kk, metric=m, id_offset=off, out=out)
+    global last_exchange
     kk = min(k, local_base.shape[0])
+    peer = None
     if world == 1:
         if kk == k:
             return local_knn(local_base, queries, k, metric, row_offset)
         sbuf = torch.empty(_chunk_bytes(nq, k), dtype=torch.uint8, device=queries.device)
+        d_loc, i_loc = _chunk_views(sbuf, nq, k)
     else:
-        sbuf, gbuf = exchange_buffers(nq, k, world, queries.device)
-    d_loc, i_loc = _chunk_views(sbuf, nq, k)
+        peer = peer_exchange(nq, k, queries.device, group) if merge is None else None
+        if peer is not None:
+            d_loc, i_loc = peer.slot()                 # the kernel writes into the exported buffer
+        else:
+            sbuf, gbuf = exchange_buffers(nq, k, world, queries.device)
+            d_loc, i_loc = _chunk_views(sbuf, nq, k)
     if kk == k:
         # the kernel writes its [Q, k] lists straight into the send chunk
         if "out" in inspect.signature(local_knn).parameters:
@@ -115,6 +233,9 @@ def sharded_knn(local_base: torch.Tensor, queries: torch.Tensor, k: int, metric:
             i_loc[:, :kk] = ii
     if world == 1:
         return d_loc, i_loc
+    if peer is not None:
+        last_exchange = "peer-memory gather+merge kernel"
+        return peer.merge(k)
     return _exchange_and_merge(sbuf, gbuf, nq, k, world, group, merge)
 
 

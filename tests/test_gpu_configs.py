@@ -147,8 +147,10 @@ def _free_port():
     return port
 
 
-def _nccl_worker(rank, world, port, nb, nq, d, k, metric, out_dir):
+def _nccl_worker(rank, world, port, nb, nq, d, k, metric, out_dir, exchange):
     sys.path.insert(0, ROOT)
+    if exchange == "allgather":
+        os.environ["NWK_EXCHANGE"] = "allgather"
     import torch
     import torch.distributed as dist
     from neighborhoodwatch_b200 import dist as nwdist
@@ -165,30 +167,34 @@ def _nccl_worker(rank, world, port, nb, nq, d, k, metric, out_dir):
             out_d, out_i = nwdist.sharded_knn(base, q, k, metric, lo)
         torch.cuda.synchronize(dev)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), d=out_d.cpu().numpy(), i=out_i.cpu().numpy(),
-                 exchange=np.array(nwdist.last_exchange or "none"))
+                 exchange=np.array(nwdist.last_exchange or "none"), why=np.array(nwdist._peer_failed or ""))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "allgather"])
 @pytest.mark.parametrize("metric,nb,d,k", [("sqeuclidean", 300_001, 1536, 100), ("cosine", 150, 64, 100)])
-def test_sharded_knn_nccl_world2(tmp_path, metric, nb, d, k):
-    """dist.sharded_knn on two GPUs (NCCL): shard, local tcgen05 top-k with global ids, exchange,
-    merge kernel -- identical on both ranks and equal to the oracle.  (150 rows over 2 ranks:
-    shards smaller than k are padded.)"""
+def test_sharded_knn_nccl_world2(tmp_path, metric, nb, d, k, exchange):
+    """dist.sharded_knn on two GPUs: shard, local tcgen05 top-k with global ids, then either the
+    peer-memory gather+merge kernel (lists read from the owners' HBM over NVLink, nwk_xchg_*) or one
+    packed NCCL all-gather + the merge kernel -- identical on both ranks and equal to the oracle.
+    (150 rows over 2 ranks: shards smaller than k are padded.)"""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     nq = 500
     port = _free_port()
-    mp.spawn(_nccl_worker, args=(2, port, nb, nq, d, k, metric, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, port, nb, nq, d, k, metric, str(tmp_path), exchange), nprocs=2, join=True)
     base, q = synth.vectors(nb, d, 1234), synth.vectors(nq, d, 5678)
     g0 = np.load(tmp_path / "r0.npz")
     g1 = np.load(tmp_path / "r1.npz")
     assert np.array_equal(g0["i"], g1["i"]) and np.array_equal(g0["d"], g1["d"])
     sel = np.arange(0, nq, 5)
     res = _check(g0["d"][sel], g0["i"][sel], base, q[sel], k, metric)
-    print(res, str(g0["exchange"]))
+    print(res, str(g0["exchange"]), str(g0["why"]))
+    want = "peer-memory gather+merge kernel" if exchange == "peer" else "packed-all-gather"
+    assert str(g0["exchange"]) == want == str(g1["exchange"]), str(g0["why"])
 
 
 def _write_vectors(path, vecs, row_group_size=257):
