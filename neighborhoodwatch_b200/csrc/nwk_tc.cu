@@ -1661,12 +1661,11 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
   if (pl.sample) {
     // the SAMPLE_M-th smallest key of a sample of every `stride`-th row has about
     // SAMPLE_M * stride rows of the whole base below it
-    // Long rows: every 64th row and the 16th smallest key (spread 1/sqrt(16) instead of 1/sqrt(32): the log
-    // holds 4 x the target): the sample pass costs 1/64 of the filter pass's FLOPs instead of 1/32.
-    // Short rows keep the denser sample: there the filter's epilogue is the limit and candidates cost more.
-    // Large query sets keep the 32-entry statistic as well: with 10^5 queries per slab the 1-in-10^5 query whose
-    // threshold comes out too low costs an fp64 scan of the slab (measured: 4 ms per 1M x 1024 slab).
-    pl.sM = (d >= 512 && nq <= 16384) ? 16 : SAMPLE_M;
+    // The threshold statistic: the SAMPLE_M-th smallest key of every 32nd row.  (Every 64th row and the 16th
+    // smallest key halve the sample pass -- measured -0.3 ms of 13.3 at config 2 -- but the wider spread of
+    // the threshold left 2 of 10 000 queries of a 5M x 1536 shard uncertified, and an uncertified query
+    // costs an fp64 scan of the whole shard: +32 ms.  NWK_SAMPLE_M=16 keeps the variant for experiments.)
+    pl.sM = SAMPLE_M;
     if (const char* e = getenv("NWK_SAMPLE_M")) pl.sM = atoi(e) <= 16 ? 16 : SAMPLE_M;     // experiment switch
     pl.s_stride = LOG_TARGET / pl.sM;
     pl.ns = (nb + pl.s_stride - 1) / pl.s_stride;
