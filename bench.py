@@ -267,7 +267,7 @@ class ShardedRun:
 
     def reset(self):
         self.stage_ms = {"prep": [], "sample": [], "filter": [], "finish": [], "fallback": [], "total": []}
-        self.agg = {"fallback": 0, "max_candidates": 0, "max_rerank": 0, "cand": 0, "rerank": 0, "err_ratio": 0.0}
+        self.agg = {"fallback": 0, "retry": 0, "max_candidates": 0, "max_rerank": 0, "cand": 0, "rerank": 0, "err_ratio": 0.0}
         self.exch = []
 
     def _local(self, b, q, kk, m, off, out=None, **kw):
@@ -278,6 +278,7 @@ class ShardedRun:
             self.stage_ms[name].append(st[f"ms_{name}"])
         a = self.agg
         a["fallback"] += st["n_fallback_queries"]
+        a["retry"] += st.get("n_retry_queries", 0)
         a["max_candidates"] = max(a["max_candidates"], st["max_candidates"])
         a["max_rerank"] = max(a["max_rerank"], st["max_rerank"])
         a["err_ratio"] = max(a["err_ratio"], st["max_err_ratio"])
@@ -511,6 +512,7 @@ def run_config3(torch, dev, n_gpus, rank, distributed, peaks, steps=5, warmup=3)
             "exchange_ms": r["exchange_ms"], "exchange": r.get("exchange"), "local_ms_max_over_ranks": r["local_ms_max"],
             "local_ms_min_over_ranks": r["local_ms_min"], "stage_ms_mean": r["stage_ms_mean"],
             "gpu_launches": r["launches"], "fallback_queries_per_step": r["agg"]["fallback"] / steps,
+            "second_chance_queries_per_step": r["agg"]["retry"] / steps,
             "sampled_queries_equal_fp64_scan": same}
 
 
@@ -642,6 +644,7 @@ def main():
             "exchange_ms_per_step": r["exchange_ms"], "exchange": r.get("exchange"),
             "local_knn_ms": {"max_over_ranks": r["local_ms_max"], "min_over_ranks": r["local_ms_min"]},
             "exactness": {"fallback_queries_per_step": agg["fallback"] / max(args.steps, 1),
+                          "second_chance_queries_per_step": agg["retry"] / max(args.steps, 1),
                           "mean_candidates_per_query": agg["cand"] / max(args.steps * nq, 1),
                           "mean_rerank_per_query": agg["rerank"] / max(args.steps * nq, 1),
                           "max_candidates": agg["max_candidates"], "max_rerank": agg["max_rerank"],

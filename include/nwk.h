@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NWK_ABI_VERSION 1
+#define NWK_ABI_VERSION 2
 
 typedef enum nwk_status {
   NWK_OK = 0,
@@ -66,7 +66,7 @@ typedef enum nwk_metric {
 /* Per-call diagnostics (all counters refer to the last nwk_knn_f32 call they were passed to). */
 typedef struct nwk_knn_stats {
   int32_t path;               /* 0 = fp64 exact scan; tcgen05 candidates + fp64 rerank: 1 = fp16, 2 = TF32; 3 = nwk_maxsim_f32 */
-  int32_t n_fallback_queries; /* queries whose candidate set could not be certified -> fp64 exact scan   */
+  int32_t n_fallback_queries; /* queries whose candidate set could not be certified (after the second chance) -> fp64 exact scan */
   int32_t max_candidates;     /* largest per-query candidate-log population seen                         */
   int32_t max_rerank;         /* largest per-query number of rows re-ranked in fp64                      */
   int64_t total_candidates;   /* sum over queries of candidate-log population                            */
@@ -80,6 +80,8 @@ typedef struct nwk_knn_stats {
   float   ms_finish;          /* select + fp64 rerank                                                    */
   float   ms_fallback;        /* fp64 scan of uncertified queries                                        */
   float   ms_total;           /* whole call                                                              */
+  int32_t n_retry_queries;    /* uncertified queries that got a second tensor-core pass at a higher threshold */
+  int32_t reserved_;
 } nwk_knn_stats;
 
 const char* nwk_last_error(void);

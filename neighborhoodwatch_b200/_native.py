@@ -22,6 +22,7 @@ FLAG_PROFILE = 0x4
 FLAG_TF32 = 0x8
 FLAG_ALPHA_BETA = 0x10
 MAX_K = 1024
+ABI_VERSION = 2
 MERGE_MAX_K = 2048
 
 # every symbol include/nwk.h declares (tests/test_abi.py checks the library exports them all)
@@ -48,10 +49,11 @@ class KnnStats(Structure):
         ("max_rerank", c_int32), ("total_candidates", c_int64), ("total_rerank", c_int64),
         ("gpu_launches", c_int32), ("max_err_ratio", c_float), ("ms_prep", c_float), ("ms_sample", c_float),
         ("ms_filter", c_float), ("ms_finish", c_float), ("ms_fallback", c_float), ("ms_total", c_float),
+        ("n_retry_queries", c_int32), ("reserved_", c_int32),
     ]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved_"}
 
 
 _lib = None
@@ -144,8 +146,8 @@ def load() -> ctypes.CDLL:
     lib.nwk_validate_pairs.restype = c_int32
     lib.nwk_validate_pairs.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32,
                                        ctypes.c_double, ctypes.c_double, POINTER(c_int64), c_void_p]
-    if lib.nwk_abi_version() != 1:
-        raise ImportError(f"{path}: ABI version {lib.nwk_abi_version()} != 1")
+    if lib.nwk_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.nwk_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -176,6 +176,7 @@ static int knn_impl(const float* base, int64_t nb, const float* query, int64_t n
                     size_t ws_bytes, uint32_t flags, nwk_knn_stats* stats, void* stream, const float* bound,
                     long long bound_stride) {
   if (!base || !query || !out_dist || !out_idx) return fail(NWK_ERR_ARG, "null pointer argument");
+  flags &= 0x7fffffffu;       // (the top bit is the library's own: a call that is a second-chance pass)
   if (nb <= 0 || nq < 0 || d <= 0) return fail(NWK_ERR_ARG, "bad shape nb=%lld nq=%lld d=%d", (long long)nb, (long long)nq, d);
   if (k <= 0 || k > NWK_MAX_K) return fail(NWK_ERR_ARG, "k=%d outside [1, %d]", k, NWK_MAX_K);
   if (k > nb) return fail(NWK_ERR_ARG, "k=%d exceeds dataset rows %lld", k, (long long)nb);
@@ -481,6 +482,7 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
         NWK_CUDA(cudaEventRecord(c.freed[b], c.comp_stream));
         total.path = s1.path;
         total.n_fallback_queries += s1.n_fallback_queries;
+        total.n_retry_queries += s1.n_retry_queries;
         total.total_candidates += s1.total_candidates;
         total.total_rerank += s1.total_rerank;
         total.gpu_launches += s1.gpu_launches;

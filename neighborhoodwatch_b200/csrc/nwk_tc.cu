@@ -77,10 +77,11 @@ constexpr int SAMPLE_MAX_LISTS = SAMPLE_MAX_PARTS * SAMPLE_WG;        // lists p
 static_assert(SAMPLE_QCAP >= 40, "the queue must take a whole 32-column chunk beyond the flush mark");
 constexpr int LOG_CAP = 4096;                  // candidate-log slots per query
 constexpr int LOG_TARGET = 1024;               // population the sampled threshold aims at
-static_assert(((LOG_TARGET / SAMPLE_M) & (LOG_TARGET / SAMPLE_M - 1)) == 0, "sample stride must be a power of two");
 constexpr int RERANK_MAX = 2048;               // most rows re-ranked in fp64 per query (fp64 results live in log slots [LOG_CAP/2, LOG_CAP))
 static_assert(RERANK_MAX <= LOG_CAP / 2, "re-ranked distances alias the upper half of the query's log");
 constexpr int TC_MAX_K = 256;
+constexpr int RETRY_MAX = 4096;                // most uncertified queries of a call that get a second tensor-core pass
+constexpr unsigned int FLAG_INTERNAL_RETRY = 0x80000000u;   // the call IS that second pass (never set by callers)
 #ifndef NWK_WARP_ARRIVE
 #define NWK_WARP_ARRIVE 1         // 1: one tempty arrival per epilogue warp, 0: one per thread
 #endif
@@ -101,7 +102,7 @@ struct TcParams {
   int nQT, nT;
   int G, nChunks, nUnits;   // FILTER: unit = (chunk of G base tiles, query tile)
   int t0;                   // FILTER: first base tile of this launch (the base may be filtered in parts; nT counts this part's tiles)
-  int sM;                   // SAMPLE: rank of the list entry that becomes the threshold (16 or SAMPLE_M)
+  int sM;                   // SAMPLE: rank of the list entry that becomes the threshold (a multiple of 4 in [8, SAMPLE_M])
   int sWarm;                // SAMPLE: 1 = start every part with the short warm-up list (large samples only)
   int nS, sChunks, sParts;  // SAMPLE: tiles of the sample matrix, chunks per tile (8), parts per query tile (<= SAMPLE_MAX_PARTS)
   const float* alpha;       // [nT*TB]   (SAMPLE mode: the sample rows' values, [nS*TB])
@@ -431,6 +432,18 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long row_begi
     }
   }
   if (lane == 0 && local_max > 0.f) atomicMax(&sc->bn2max, __float_as_uint(local_max));
+}
+
+// entry of rank m (1-based; m a multiple of 4 in [8, SAMPLE_M]) of a register-resident sorted list
+__device__ __forceinline__ float list_rank(const float (&lst)[SAMPLE_M], int m) {
+  float v = lst[SAMPLE_M - 1];
+  v = m <= 28 ? lst[27] : v;
+  v = m <= 24 ? lst[23] : v;
+  v = m <= 20 ? lst[19] : v;
+  v = m <= 16 ? lst[15] : v;
+  v = m <= 12 ? lst[11] : v;
+  v = m <= 8 ? lst[7] : v;
+  return v;
 }
 
 // tau_q = m-th smallest key (m <= SAMPLE_M) of the union of the query's per-part lists (one warp per
@@ -818,7 +831,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
           lst[0] = fminf(lst[0], key);
         }
         cnt = 0;
-        tau = fminf(tau, p.sM <= 16 ? lst[15] : lst[SAMPLE_M - 1]);
+        tau = fminf(tau, list_rank(lst, p.sM));
       };
       auto chunk = [&](const uint32_t (&cur)[32], int ch) {
         if (warm < SAMPLE_WARM) {                           // warp-uniform
@@ -1562,6 +1575,43 @@ output_kernel(const FinParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// second chance: the queries of a fail list as a compact query set, and their results back
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+retry_gather_kernel(const float* __restrict__ query, const int* __restrict__ list, int n, int d,
+                    const float* __restrict__ bound, long long bound_stride, float* __restrict__ rq,
+                    float* __restrict__ rbound, int* __restrict__ rlist) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+    const long long q = list[i];
+    for (int c = lane; c < d; c += 32) rq[(long long)i * d + c] = query[q * d + c];
+    if (lane == 0) {
+      rlist[i] = (int)q;
+      if (bound) rbound[i] = bound[q * bound_stride];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+retry_scatter_kernel(const float* __restrict__ rd, const long long* __restrict__ ri, const int* __restrict__ rlist, int n,
+                     int k, float* __restrict__ out_dist, long long* __restrict__ out_idx) {
+  const long long total = (long long)n * k;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / k), j = (int)(t - (long long)i * k);
+    const long long q = rlist[i];
+    out_dist[q * k + j] = rd[t];
+    out_idx[q * k + j] = ri[t];
+  }
+}
+
+// a retry keeps the scales and the prepared base of its parent call: only the per-call counters start over
+__global__ void retry_reset_kernel(Scalars* sc) {
+  sc->fail_cnt = 0;
+  sc->stat_max[0] = sc->stat_max[1] = 0u;
+  sc->stat_sum[0] = sc->stat_sum[1] = 0ull;
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1628,14 +1678,14 @@ bool tc_path_supported(long long nb, long long nq, int d, int k) {
 
 struct TcPlan {
   int nQT, nT, nKB, kLast, G, nChunks, nUnits, nS, sChunks, sParts, dh, kcols, pitch, sM;
+  bool retry_ok;            // the first pass uses a rank below SAMPLE_M: uncertified queries get a second chance at SAMPLE_M
   bool sample;
   long long nb_pad, nq_pad;
   long long s_stride, ns, ns_pad;
 };
 
 // xcols = extra K columns of the fp16 operand copies (L2X_COLS for direct squared-L2 keys)
-static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16, int xcols = 0) {
-  (void)k;
+static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool f16, int xcols = 0, int first_rank_override = 0) {
   TcPlan pl{};
   const int bk = f16 ? 64 : 32;
   pl.dh = (d + 7) / 8 * 8;
@@ -1658,16 +1708,35 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
   // sampling only pays when the base is larger than what the log can simply hold
   pl.sample = nb > LOG_CAP / 2;
   pl.sM = SAMPLE_M;
+  pl.retry_ok = false;
   if (pl.sample) {
     // the SAMPLE_M-th smallest key of a sample of every `stride`-th row has about
     // SAMPLE_M * stride rows of the whole base below it
-    // The threshold statistic: the SAMPLE_M-th smallest key of every 32nd row.  (Every 64th row and the 16th
-    // smallest key halve the sample pass -- measured -0.3 ms of 13.3 at config 2 -- but the wider spread of
-    // the threshold left 2 of 10 000 queries of a 5M x 1536 shard uncertified, and an uncertified query
-    // costs an fp64 scan of the whole shard: +32 ms.  NWK_SAMPLE_M=16 keeps the variant for experiments.)
-    pl.sM = SAMPLE_M;
-    if (const char* e = getenv("NWK_SAMPLE_M")) pl.sM = atoi(e) <= 16 ? 16 : SAMPLE_M;     // experiment switch
-    pl.s_stride = LOG_TARGET / pl.sM;
+    // The threshold statistic: the sM-th smallest key of a stratified sample of every s_stride-th row has
+    // about sM * s_stride rows of the whole base below it, with a relative spread of 1 / sqrt(sM).
+    //   long rows  (d >= 512): every 64th row, rank 16 -> ~1024 candidates per query; the sample pass costs
+    //              1/64 of the filter pass's FLOPs (measured -0.3 ms of 13.3 at config 2 against 32 / 32);
+    //   short rows: every 32nd row, rank 12 -> ~384 candidates: there the filter's epilogue is the limit
+    //              and every candidate costs a trip through its slow path (and 8 bytes of log traffic).
+    // The rank grows with k so that about 3.5 k rows pass.  A low rank leaves the odd query with a threshold
+    // below what its band needs (2 of 10 000 at rank 16 on a 5M x 1536 shard); such a query used to cost an
+    // fp64 scan of the whole base (+32 ms there) and now gets a SECOND CHANCE: the same sample at rank
+    // SAMPLE_M (twice to three times the candidates), one more tensor-core pass over the base for the
+    // handful of uncertified queries (tc_knn's retry).  Only what fails again goes to the scan.
+    // Small bases keep the dense, high-rank statistic: their sample pass costs microseconds, while a second
+    // chance costs a dozen launches and a host round trip (measured at config 1, 1000 x 10 000 x 384:
+    // 0.33 ms per call with rank 32, 0.43 ms with rank 12 and its 4 second-chance queries).
+    const bool small = nb < 200000;
+    pl.s_stride = (d >= 512 && !small) ? 64 : 32;
+    int rank = small ? SAMPLE_M : (d >= 512 ? 16 : 12);
+    const int need = (int)((7ll * k / 2 + pl.s_stride - 1) / pl.s_stride);
+    if (rank < need) rank = need;
+    if (const char* e = getenv("NWK_SAMPLE_M")) rank = atoi(e);                              // experiment switches
+    if (const char* e = getenv("NWK_SAMPLE_STRIDE")) pl.s_stride = atoi(e) >= 64 ? 64 : 32;
+    rank = (rank + 3) / 4 * 4;
+    pl.sM = rank < 8 ? 8 : (rank > SAMPLE_M ? SAMPLE_M : rank);
+    if (first_rank_override > 0) pl.sM = first_rank_override;
+    pl.retry_ok = pl.sM < SAMPLE_M;
     pl.ns = (nb + pl.s_stride - 1) / pl.s_stride;
     pl.ns_pad = (pl.ns + TB - 1) / TB * TB;
     pl.nS = (int)(pl.ns_pad / TB);
@@ -1686,25 +1755,65 @@ static TcPlan make_plan(long long nb, long long nq, int d, int k, int sms, bool 
   return pl;
 }
 
+// Workspace layout: [base-dependent buffers][retry area][query-dependent buffers][fp64 scan scratch].
+// The first two depend on (nb, d, k) only, so the second-chance call (same base, a few queries) finds the
+// prepared base where its parent left it and may reuse the parent's query-dependent region.
+struct TcArena {
+  // base-dependent
+  float *alpha, *beta, *salpha, *sbeta, *srows;
+  __half* bh;
+  Scalars* sc;
+  // retry area
+  float *rq, *rbound, *rout_d;
+  long long* rout_i;
+  int* rlist;
+  // query-dependent
+  float *tau, *epsq, *slist;
+  unsigned int* cnt;
+  unsigned long long* log;
+  int *fail_list, *rr, *rr2;
+  double* qn2;
+  unsigned char* bflag;
+  __half* qh;
+  size_t end;
+};
+
+static TcArena carve(void* ws, size_t ws_bytes, const TcPlan& pl, long long nb, long long nq, int d, int k) {
+  Arena ar(ws, ws_bytes);
+  TcArena a{};
+  a.alpha = ar.take<float>((size_t)pl.nb_pad);
+  a.beta = ar.take<float>((size_t)pl.nb_pad);
+  a.bh = ar.take<__half>((size_t)nb * pl.pitch);
+  a.salpha = ar.take<float>((size_t)pl.ns_pad);
+  a.sbeta = ar.take<float>((size_t)pl.ns_pad);
+  a.srows = ar.take<float>((size_t)(pl.ns + 1) * (size_t)(d > pl.pitch ? d : pl.pitch));
+  a.sc = ar.take<Scalars>(1);
+  a.rq = ar.take<float>((size_t)RETRY_MAX * d);
+  a.rbound = ar.take<float>((size_t)RETRY_MAX);
+  a.rout_d = ar.take<float>((size_t)RETRY_MAX * k);
+  a.rout_i = ar.take<long long>((size_t)RETRY_MAX * k);
+  a.rlist = ar.take<int>((size_t)RETRY_MAX);
+  a.tau = ar.take<float>((size_t)pl.nq_pad);
+  a.cnt = ar.take<unsigned int>((size_t)nq);
+  a.log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
+  a.fail_list = ar.take<int>((size_t)nq);
+  a.rr = ar.take<int>((size_t)nq);
+  a.rr2 = ar.take<int>((size_t)nq);
+  a.epsq = ar.take<float>((size_t)nq);
+  a.qn2 = ar.take<double>((size_t)nq);
+  a.bflag = ar.take<unsigned char>((size_t)nq);
+  a.slist = ar.take<float>((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M);
+  a.qh = ar.take<__half>((size_t)nq * pl.pitch);
+  a.end = align_up(ar.off, 256);
+  return a;
+}
+
 size_t tc_workspace_bytes(long long nb, long long nq, int d, int k) {
+  // (the widest variant: direct squared-L2 keys add L2X_COLS columns to the operand copies)
   TcPlan pl = make_plan(nb, nq, d, k, 148, true, L2X_COLS);
-  size_t bytes = 0;
-  bytes += align_up((size_t)pl.nb_pad * 4, 256) * 2;        // alpha, beta
-  bytes += align_up((size_t)pl.nq_pad * 4, 256);            // tau
-  bytes += align_up((size_t)nq * 4, 256);                   // cnt
-  bytes += align_up((size_t)nq * LOG_CAP * 8, 256);         // log
-  bytes += align_up((size_t)nq * 4, 256) * 4;               // fail list, rows-to-rerank (two bands), eps
-  bytes += align_up((size_t)nq * 8, 256);                   // |q|^2
-  bytes += align_up((size_t)nq, 256);                       // bound flags
-  bytes += align_up((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M * 4, 256);    // per-part, per-warpgroup sample lists
-  bytes += align_up((size_t)nb * pl.pitch * 2, 256);        // fp16 base
-  bytes += align_up((size_t)nq * pl.pitch * 2, 256);        // fp16 queries
-  bytes += align_up((size_t)pl.ns_pad * 4, 256) * 2;        // sample alpha, beta
-  bytes += align_up((size_t)(pl.ns + 1) * (size_t)(d > pl.pitch ? d : pl.pitch) * 4, 256);   // sample rows (fp16 or fp32)
-  bytes += 4096;                                            // scalars
+  const TcArena a = carve(nullptr, 0, pl, nb, nq, d, k);
   // fallback scan for up to 64 queries is always provisioned; more is handled in rounds
-  bytes += exact_scan_workspace_bytes(nb, 64, k) + 256;
-  return bytes + 4096;
+  return a.end + exact_scan_workspace_bytes(nb, 64, k) + 256 + 4096;
 }
 
 template <bool F16>
@@ -1734,30 +1843,21 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   bool direct = f16 && !(flags & NWK_FLAG_ALPHA_BETA) && (metric == NWK_METRIC_COSINE || (d + 7) / 8 * 8 <= 256);
   if (const char* e = getenv("NWK_DIRECT")) direct = f16 && !(flags & NWK_FLAG_ALPHA_BETA) && atoi(e) != 0;   // experiment switch
   const bool l2x = direct && metric == NWK_METRIC_SQEUCLIDEAN;
-  TcPlan pl = make_plan(nb, nq, d, k, sms, f16, l2x ? L2X_COLS : 0);
-  Arena ar(ws, ws_bytes);
-  float* alpha = ar.take<float>((size_t)pl.nb_pad);
-  float* beta = ar.take<float>((size_t)pl.nb_pad);
-  float* tau = ar.take<float>((size_t)pl.nq_pad);
-  unsigned int* cnt = ar.take<unsigned int>((size_t)nq);
-  unsigned long long* log = ar.take<unsigned long long>((size_t)nq * LOG_CAP);
-  int* fail_list = ar.take<int>((size_t)nq);
-  int* rr = ar.take<int>((size_t)nq);
-  int* rr2 = ar.take<int>((size_t)nq);
-  float* epsq = ar.take<float>((size_t)nq);
-  double* qn2 = ar.take<double>((size_t)nq);
-  unsigned char* bflag = ar.take<unsigned char>((size_t)nq);
-  float* slist = ar.take<float>((size_t)nq * SAMPLE_MAX_LISTS * SAMPLE_M);
-  __half* bh = ar.take<__half>((size_t)nb * pl.pitch);
-  __half* qh = ar.take<__half>((size_t)nq * pl.pitch);
-  float* salpha = ar.take<float>((size_t)pl.ns_pad);
-  float* sbeta = ar.take<float>((size_t)pl.ns_pad);
-  float* srows = ar.take<float>((size_t)(pl.ns + 1) * (size_t)(d > pl.pitch ? d : pl.pitch));
-  Scalars* sc = ar.take<Scalars>(1);
-  ar.off = align_up(ar.off, 256);
-  void* scan_ws = ar.base + ar.off;
-  if (ar.off > ws_bytes) return fail(NWK_ERR_WORKSPACE, "workspace too small for the tensor-core path");
-  size_t scan_ws_bytes = ws_bytes - ar.off;
+  const bool retry = (flags & FLAG_INTERNAL_RETRY) != 0;
+  TcPlan pl = make_plan(nb, nq, d, k, sms, f16, l2x ? L2X_COLS : 0, retry ? SAMPLE_M : 0);
+  const TcArena wa = carve(ws, ws_bytes, pl, nb, nq, d, k);
+  float *alpha = wa.alpha, *beta = wa.beta, *tau = wa.tau, *epsq = wa.epsq, *slist = wa.slist;
+  float *salpha = wa.salpha, *sbeta = wa.sbeta, *srows = wa.srows;
+  unsigned int* cnt = wa.cnt;
+  unsigned long long* log = wa.log;
+  int *fail_list = wa.fail_list, *rr = wa.rr, *rr2 = wa.rr2;
+  double* qn2 = wa.qn2;
+  unsigned char* bflag = wa.bflag;
+  __half *bh = wa.bh, *qh = wa.qh;
+  Scalars* sc = wa.sc;
+  if (wa.end > ws_bytes) return fail(NWK_ERR_WORKSPACE, "workspace too small for the tensor-core path");
+  void* scan_ws = static_cast<char*>(ws) + wa.end;
+  size_t scan_ws_bytes = ws_bytes - wa.end;
 
   // Filter variant.  CTA pairs (cta_group::2) when the query tiles pair up without much waste and
   // the MMAs of a tile outlast its epilogue (measured: -6 % filter time at d = 768, -10 % at
@@ -1776,27 +1876,35 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     for (int i = 0; i < 6; ++i) cudaEventCreate(&ev[i]);
     cudaEventRecord(ev[0], s);
   }
-  NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
+  if (retry) {
+    // second chance: the scales in `sc`, the fp16 base, alpha / beta and the sample matrix are the parent call's
+    retry_reset_kernel<<<1, 1, 0, s>>>(sc);
+    NWK_LAUNCH_CHECK();
+  } else {
+    NWK_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
+  }
   NWK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, s));
 
   if (f16) {
-    qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
-    NWK_LAUNCH_CHECK();
-    if (l2x) {
-      qnorm_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, &sc->qn2max);
+    if (!retry) {
+      qmax_kernel<<<sms, 256, 0, s>>>(query, nq * d, &sc->qabsmax);
       NWK_LAUNCH_CHECK();
+      if (l2x) {
+        qnorm_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, &sc->qn2max);
+        NWK_LAUNCH_CHECK();
+      }
     }
     qprep_kernel<<<sms * 2, 256, 0, s>>>(query, nq, d, pl.dh, pl.pitch, metric, direct ? 1 : 0, sc, qh);
     NWK_LAUNCH_CHECK();
   }
-  if (direct && metric == NWK_METRIC_DOT) {
+  if (direct && metric == NWK_METRIC_DOT && !retry) {
     // the one extra pass the direct keys cost: the global scale needs max |b_ij| before any row is converted
     qmax_kernel<<<sms * 8, 256, 0, s>>>(base, nb * d, &sc->babsmax);
     NWK_LAUNCH_CHECK();
   }
   SampleOut no_sample{};
   no_sample.stride_log2 = -1;
-  if (pl.sample) {
+  if (pl.sample && !retry) {
     // the sample rows first (1/32 .. 1/64 of the base): the sample pass can start while the bulk of the
     // base is still being prepared
     SampleOut so{};
@@ -1834,7 +1942,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     if (roomy && units_total >= (long long)workers * 24) nparts = 3;
     else if (roomy && units_total >= (long long)workers * 12) nparts = 2;
     if (const char* e = getenv("NWK_PARTS")) nparts = std::max(1, std::min(8, atoi(e)));     // experiment switch
-    if (nparts > (pl.nT + G - 1) / G) nparts = 1;
+    if (nparts > (pl.nT + G - 1) / G || retry) nparts = 1;
   }
   int part_t0[9];
   {
@@ -1853,7 +1961,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     NWK_CUDA(cudaEventRecord(ds->ev_fork, s));
     NWK_CUDA(cudaStreamWaitEvent(sp, ds->ev_fork, 0));
   }
-  for (int pi = 0; pi < nparts; ++pi) {
+  for (int pi = 0; pi < nparts && !retry; ++pi) {
     const long long r0 = (long long)part_t0[pi] * TB;
     const long long r1 = pi == nparts - 1 ? pl.nb_pad : (long long)part_t0[pi + 1] * TB;
     // beside a 384-thread filter CTA (12 warps x 4096 registers) an SM has 16 K registers left: 4-warp
@@ -2043,9 +2151,20 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (err_ratio > 1.0f)
     return fail(NWK_ERR_INTERNAL, "candidate keys exceeded the proven error bound (ratio %.3f)", err_ratio);
 
+  int n_retried = 0, n_scanned = h.fail_cnt;
+  nwk_knn_stats st2{};
   if (h.fail_cnt > 0 && !(flags & NWK_FLAG_NO_FALLBACK) && p.dbg == 0) {
-    // uncertified queries: fp64 scan, in rounds that fit the provisioned scratch
-    long long done = 0;
+    // Uncertified queries.  Where the first pass used a low threshold rank they get a second chance first:
+    // the same pipeline for just these queries (one or a few query tiles: a pass over the fp16 base at HBM
+    // speed instead of an fp64 scan of the fp32 base per 8 queries), with the threshold taken at rank SAMPLE_M.
+    long long scan_from = 0;
+    if (!retry && pl.retry_ok && pl.sample && !getenv("NWK_NO_RETRY")) {
+      n_retried = (int)std::min<long long>(h.fail_cnt, RETRY_MAX);
+      scan_from = n_retried;
+    }
+    // fp64 scan, in rounds that fit the provisioned scratch (first: the second chance below reuses this
+    // call's query-dependent buffers, the fail list among them)
+    long long done = scan_from;
     while (done < h.fail_cnt) {
       long long n = h.fail_cnt - done;
       while (n > 8 && exact_scan_workspace_bytes(nb, n, k) > scan_ws_bytes) n = (n + 1) / 2;
@@ -2055,12 +2174,26 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
                          scan_ws, scan_ws_bytes, s));
       done += n;
     }
+    n_scanned = (int)(h.fail_cnt - scan_from);
+    if (n_retried > 0) {
+      retry_gather_kernel<<<(n_retried + 7) / 8, 256, 0, s>>>(query, fail_list, n_retried, d, bound, bound_stride, wa.rq,
+                                                             wa.rbound, wa.rlist);
+      NWK_LAUNCH_CHECK();
+      NWK_TRY(tc_knn(base, nb, wa.rq, n_retried, d, k, metric, id_offset, wa.rout_d, wa.rout_i, ws, ws_bytes,
+                     (flags | FLAG_INTERNAL_RETRY) & ~NWK_FLAG_PROFILE, &st2, s, bound ? wa.rbound : nullptr, 1));
+      retry_scatter_kernel<<<std::min((n_retried * k + 255) / 256, sms * 8), 256, 0, s>>>(wa.rout_d, wa.rout_i, wa.rlist,
+                                                                                       n_retried, k, out_dist, out_idx);
+      NWK_LAUNCH_CHECK();
+      n_scanned += st2.n_fallback_queries;
+      if (st2.max_err_ratio > err_ratio) err_ratio = st2.max_err_ratio;
+    }
   }
   if (profile) cudaEventRecord(ev[5], s);
   NWK_CUDA(cudaStreamSynchronize(s));
   if (stats) {
     stats->path = f16 ? 1 : 2;
-    stats->n_fallback_queries = h.fail_cnt;
+    stats->n_fallback_queries = n_scanned;      // queries that took the fp64 scan
+    stats->n_retry_queries = n_retried;         // queries that got a second tensor-core pass (some of them scanned after it)
     stats->max_candidates = (int)h.stat_max[0];
     stats->max_rerank = (int)h.stat_max[1];
     stats->total_candidates = (long long)h.stat_sum[0];

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in nwk.h but not exported by libnwk.so"
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
-    assert lib.nwk_abi_version() == 1
+    assert lib.nwk_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_library_is_in_tree_and_native_only():
