@@ -531,6 +531,7 @@ def main():
     ap.add_argument("--c4-queries", type=int, default=100_000)
     ap.add_argument("--c4-rows-per-gpu", type=int, default=12_500_000)
     ap.add_argument("--c4-slab-rows", type=int, default=1_000_000)
+    ap.add_argument("--c4-host-wc", action="store_true", help="keep the pinned host shard in write-combined memory")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

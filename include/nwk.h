@@ -191,6 +191,10 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
  * is folded into the slab before it).  slab_rows_in == 0 picks the default. */
 int nwk_host_slab_plan(int64_t nb, int64_t nq, int32_t d, int32_t k, int64_t slab_rows_in,
                        int64_t* slab_rows, int64_t* nslab, int64_t* last_rows);
+/* Pinned (page-locked) host memory for the arrays nwk_knn_host_f32 streams from; write_combined != 0 maps
+ * it write-combined (fast for DMA, slow for CPU reads).  Free with nwk_host_free. */
+int nwk_host_alloc(size_t bytes, int32_t write_combined, void** out);
+int nwk_host_free(void* p);
 /* The host path keeps its device staging ring, workspace and running state per device between
  * calls (no allocation once they have grown to the shapes in use); this frees them. */
 int nwk_host_release(void);
@@ -202,11 +206,14 @@ int nwk_host_release(void);
  * the Python driver uses one torch.distributed all-gather at start-up) and map them with
  * nwk_xchg_open_peers (CUDA IPC).  Per step: write the local top-k (nwk_knn_f32 with out_dist /
  * out_idx = the pointers of nwk_xchg_next_slot, ids global), then nwk_xchg_merge: it publishes the
- * rank's step counter, waits -- on the device, bounded -- until every peer has published the same
- * step, and merges the world lists of each query straight out of the owners' memory over NVLink
- * into out_dist / out_idx [nq, k_out] (ordered by (distance, id), padding = negative ids, as
- * nwk_merge_topk).  No collective library call and no staging copy on the step path; all ranks
- * must call nwk_xchg_merge the same number of times.  Replaces, across GPUs, what
+ * rank's step counter; the rank's merge kernel waits -- on the device, bounded -- until every peer
+ * has published the same step, merges ITS SLICE of the queries (nq / world of them) reading the
+ * world lists of each query straight out of the owners' memory over NVLink, and stores the merged
+ * rows into every rank's result buffer; once all ranks have done so the [nq, k_out] result
+ * (ordered by (distance, id), padding = negative ids, as nwk_merge_topk; k_out <= k) is copied to
+ * out_dist / out_idx.  Every record crosses the fabric once (an all-gather moves it world - 1
+ * times); no collective library call, no staging copy and no host round trip on the step path.
+ * All ranks must call nwk_xchg_merge the same number of times.  Replaces, across GPUs, what
  * merge_indices_and_distances (merge.py:56-101) does across the reference's base batches.
  * nwk_xchg_check reports a timed-out wait (a rank that never published). */
 typedef struct nwk_xchg nwk_xchg;

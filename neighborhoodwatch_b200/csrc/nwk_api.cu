@@ -510,6 +510,26 @@ int nwk_knn_host_f32(const float* base_host, int64_t nb, const float* query_host
   return rc;
 }
 
+// Pinned host memory for the vectors the host path streams from.  write_combined: the pages are mapped
+// write-combined on the CPU (slow for the CPU to read, but host -> device DMA reads of them need no cache
+// snooping -- worth measuring where several GPUs pull from one host, see scripts/h2d_probe.py).
+int nwk_host_alloc(size_t bytes, int32_t write_combined, void** out) {
+  if (!out || bytes == 0) return fail(NWK_ERR_ARG, "bad host allocation request");
+  NWK_TRY(device_check());
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+  if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  *out = p;
+  return NWK_OK;
+}
+
+int nwk_host_free(void* p) {
+  if (!p) return NWK_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return fail(NWK_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
+  return NWK_OK;
+}
+
 // Frees what the host path has cached on the current device (staging ring, workspace, running state).
 int nwk_host_release(void) {
   int dev = 0;

@@ -244,6 +244,33 @@ class RunningTopK:
             pass
 
 
+class PinnedArray:
+    """``[rows, d]`` fp32 pinned host memory from ``nwk_host_alloc`` (optionally write-combined), exposed as a
+    numpy array (``.array``); freed with the object."""
+
+    def __init__(self, shape, write_combined: bool = False, dtype="float32"):
+        import numpy as np
+        self._lib = _native.load()
+        self.shape = tuple(int(x) for x in shape)
+        nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        self._ptr = ctypes.c_void_p()
+        _native.check(self._lib.nwk_host_alloc(nbytes, 1 if write_combined else 0, ctypes.byref(self._ptr)))
+        buf = (ctypes.c_char * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self._lib.nwk_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def knn_host(base, queries, k: int, metric: str = "sqeuclidean", id_offset: int = 0, slab_rows: int = 0,
              out=None, force_exact_scan: bool = False):
     """Host-buffer entry point (nwk_knn_host_f32): numpy / pinned-torch arrays in, numpy out.

@@ -71,7 +71,12 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
         torch.cuda.synchronize(dev)
 
     t_fill0 = time.perf_counter()
-    base_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
+    wc = bool(getattr(args, "c4_host_wc", False))
+    if wc:
+        holder = knn.PinnedArray((rows, d), write_combined=True)
+        base_host = torch.from_numpy(holder.array)
+    else:
+        base_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
     q_host = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
     out_d_host = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
     out_i_host = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
@@ -209,6 +214,7 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
                                    f"streamed from pinned host memory in slabs of {slab} rows",
                        "queries": nq, "base_rows_total": nb_total, "base_rows_per_gpu": rows, "d": d, "k": k,
                        "metric": metric, "slab_rows": slab, "note": note,
+                       "host_memory": "pinned, write-combined" if wc else "pinned",
                        "l2": "inputs_exceed_l2 (a slab is %.1f GB)" % (slab * d * 4 / 1e9)},
             "clocks": clocks, "gpu_launches": int(lt.item()),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": (rows * d * 4 + nq * d * 4) * n_gpus,
