@@ -76,6 +76,7 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.nvml = None
         self.sm_max = None
+        self.window = []
 
     def start(self):
         try:
@@ -89,6 +90,9 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            # (the first NVML queries of a process take tens of milliseconds: pay that before the timed region)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetPowerUsage(self.handle)
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return
@@ -114,7 +118,7 @@ class ClockSampler:
                     rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                 except Exception:  # noqa: BLE001
                     rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.samples.append((sm, pw, rs))
+                self.samples.append((sm, pw, rs, time.perf_counter()))
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(0.004)
@@ -122,6 +126,15 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Start (first call) / end (second call) of the timed region, for the per-window sample count."""
+        self.window.append(time.perf_counter())
+
+    def in_window(self) -> int:
+        if len(self.window) < 2:
+            return 0
+        return sum(1 for s in self.samples if len(s) > 3 and self.window[0] <= s[3] <= self.window[1])
 
     def stop(self) -> dict:
         if self.nvml is not None:
@@ -140,8 +153,8 @@ class ClockSampler:
                 cut = statistics.median(power)
                 loaded = [c for c, pw in zip(sm, power) if pw >= cut] or sm
             return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": self.sm_max,
-                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
-                    "source": "nvml"}
+                    "power_w_max": max(power) if power else None, "samples": len(sm),
+                    "samples_in_timed_region": self.in_window(), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -327,16 +340,40 @@ class ShardedRun:
         self.barrier()
         launches0 = _native.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.mark()
         ev0.record()
         for _ in range(steps):
             out = self.step()
         ev1.record()
         self.barrier()
-        clocks = sampler.stop() if sampler else None
+        if sampler:
+            sampler.mark()
         launches = _native.launch_count() - launches0
+        stage_snap = {n: list(v) for n, v in self.stage_ms.items()}
+        agg_snap = dict(self.agg)
+        exch_snap = list(self.exch)
+        # a short timed region yields few NVML samples: keep the same load running (untimed) until the
+        # sampler has seen at least 0.4 s of it, so the reported clock is a median under load
+        extra = torch.tensor([1 if (sampler and sampler.in_window() < 24) else 0], device=self.dev)
+        if self.distributed:
+            dist.broadcast(extra, src=0)
+        if int(extra.item()):
+            t_end = time.perf_counter() + 0.4
+            while True:
+                self.step()
+                go = torch.tensor([1 if time.perf_counter() < t_end else 0], device=self.dev)
+                if self.distributed:
+                    dist.broadcast(go, src=0)
+                if not int(go.item()):
+                    break
+            self.torch.cuda.synchronize(self.dev)
+        clocks = sampler.stop() if sampler else None
+        if clocks is not None and int(extra.item()):
+            clocks["note"] = "timed region shorter than 24 NVML samples: the same steps were repeated (untimed) for 0.4 s while sampling"
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev, dtype=torch.float64)
         lt = torch.tensor([launches], device=self.dev, dtype=torch.int64)
-        local_ms = statistics.mean(self.stage_ms["total"]) if self.stage_ms["total"] else 0.0
+        local_ms = statistics.mean(stage_snap["total"]) if stage_snap["total"] else 0.0
         lmax = torch.tensor([local_ms], device=self.dev, dtype=torch.float64)
         lmin = lmax.clone()
         if self.distributed:
@@ -346,7 +383,7 @@ class ShardedRun:
             dist.all_reduce(lmin, op=dist.ReduceOp.MIN)
         exchange_ms = None
         if self.distributed:
-            pairs_ev = [ev for ev in self.exch if len(ev) == 2]
+            pairs_ev = [ev for ev in exch_snap if len(ev) == 2]
             if pairs_ev:
                 exchange_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs_ev)
         from neighborhoodwatch_b200 import dist as nwdist
@@ -354,8 +391,8 @@ class ShardedRun:
                 "exchange": (nwdist.last_exchange if self.distributed else None) if not nwdist._peer_failed
                 else f"{nwdist.last_exchange} (peer memory unavailable: {nwdist._peer_failed})",
                 "exchange_ms": exchange_ms, "local_ms_max": float(lmax.item()), "local_ms_min": float(lmin.item()),
-                "stage_ms_mean": {n: (statistics.mean(v) if v else None) for n, v in self.stage_ms.items()},
-                "agg": dict(self.agg)}
+                "stage_ms_mean": {n: (statistics.mean(v) if v else None) for n, v in stage_snap.items()},
+                "agg": agg_snap}
 
     def free(self):
         from neighborhoodwatch_b200 import dist as nwdist
@@ -623,6 +660,9 @@ def main():
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a step; fp16 and bf16 "
                                f"share the tensor-pipe rate); burst = {peaks['bf16_burst']}",
                 "flop_per_launch": flops, "ms_per_launch": filt, "traffic": None,
+                "launch_note": "the filter pass of a step is up to three launches of this kernel (parts of the base, on two "
+                               "streams, each behind its part of the preparation); flop_per_launch / ms_per_launch are the "
+                               "step's total FLOPs and the CUDA-event time from the first launch to the join of the last",
                 "stage_ms_mean": r["stage_ms_mean"]}
     for tname in ("r02_traffic.json", "r01_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
