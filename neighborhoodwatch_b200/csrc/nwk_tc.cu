@@ -1951,6 +1951,8 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     part_t0[0] = 0;
     for (int pi = 1; pi <= nparts; ++pi) {
       long long c = nparts == 1 ? chunks : (long long)chunks * (2 * pi - 1) / (2 * nparts - 1);
+      if (const char* e = getenv("NWK_PART0_PCT"))                                          // experiment switch
+        c = (long long)chunks * atoi(e) / 100 + (long long)(chunks - chunks * atoi(e) / 100) * (pi - 1) / (nparts - 1 > 0 ? nparts - 1 : 1);
       if (pi == nparts) c = chunks;
       part_t0[pi] = (int)std::min<long long>((long long)c * G, pl.nT);
     }
@@ -1961,7 +1963,7 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     NWK_CUDA(cudaEventRecord(ds->ev_fork, s));
     NWK_CUDA(cudaStreamWaitEvent(sp, ds->ev_fork, 0));
   }
-  for (int pi = 0; pi < nparts && !retry; ++pi) {
+  auto launch_prep = [&](int pi) -> int {
     const long long r0 = (long long)part_t0[pi] * TB;
     const long long r1 = pi == nparts - 1 ? pl.nb_pad : (long long)part_t0[pi + 1] * TB;
     // beside a 384-thread filter CTA (12 warps x 4096 registers) an SM has 16 K registers left: 4-warp
@@ -1972,7 +1974,15 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     else baseprep_kernel<false><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     if (prep_aside) NWK_CUDA(cudaEventRecord(ds->ev_chunk[pi], sp));
-  }
+    return NWK_OK;
+  };
+  // All parts are enqueued at once: the preparation runs beside the sample pass and the first filter launch.
+  // (Holding parts 1.. back until the thresholds exist -- NWK_PREP_GATE=1 -- shortens the sample pass, 0.78 ->
+  // 0.49 ms at config 2, and lengthens the filter pass by as much, 10.24 -> 10.62 ms: the HBM traffic of the
+  // preparation costs the tensor kernels the same time wherever it is placed.  Measured, profiles/r02_summary.md.)
+  bool gate = false;
+  if (const char* e = getenv("NWK_PREP_GATE")) gate = prep_aside && pl.sample && !bound && atoi(e) != 0;    // experiment switch
+  for (int pi = 0; pi < (gate ? 1 : nparts) && !retry; ++pi) NWK_TRY(launch_prep(pi));
   if (profile) cudaEventRecord(ev[1], s);
 
   CUtensorMap tm_q, tm_b;
@@ -2052,6 +2062,10 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   if (nparts > 1) {
     NWK_CUDA(cudaEventRecord(ds->ev_fork, s));          // thresholds are ready
     NWK_CUDA(cudaStreamWaitEvent(sf, ds->ev_fork, 0));
+    if (gate) {
+      NWK_CUDA(cudaStreamWaitEvent(sp, ds->ev_fork, 0));
+      for (int pi = 1; pi < nparts; ++pi) NWK_TRY(launch_prep(pi));
+    }
   }
   for (int pi = 0; pi < nparts; ++pi) {
     cudaStream_t sl = (pi & 1) ? sf : s;
