@@ -77,17 +77,27 @@ class ClockSampler:
         self.nvml = None
         self.sm_max = None
         self.window = []
+        self.load_end = float("inf")
 
     def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical order; honour CUDA_VISIBLE_DEVICES when it is a plain index list
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = self.gpu_index
-            if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
-                idx = int(vis.split(",")[self.gpu_index])
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            # NVML enumerates in PCI order, CUDA need not: find this rank's GPU by its PCI address
+            self.handle = None
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(self.gpu_index)
+                bdf = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            except Exception:  # noqa: BLE001
+                self.handle = None
+            if self.handle is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = self.gpu_index
+                if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
+                    idx = int(vis.split(",")[self.gpu_index])
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
             # (the first NVML queries of a process take tens of milliseconds: pay that before the timed region)
@@ -145,9 +155,14 @@ class ClockSampler:
                      "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                      "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                      "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-            sm = [s[0] for s in self.samples]
-            power = [s[1] for s in self.samples]
-            reasons = sorted(n for n, bit in names.items() if any(s[2] & bit for s in self.samples))
+            smp = self.samples
+            if self.window:
+                # under load: from 150 ms after the timed region began (NVML's readings lag) to the end of the load
+                late = [x for x in smp if x[3] >= self.window[0] + 0.15 and x[3] <= self.load_end]
+                smp = late or [x for x in smp if x[3] >= self.window[0]] or smp
+            sm = [s[0] for s in smp]
+            power = [s[1] for s in smp]
+            reasons = sorted(n for n, bit in names.items() if any(s[2] & bit for s in smp))
             loaded = sm
             if power:
                 cut = statistics.median(power)
@@ -353,13 +368,15 @@ class ShardedRun:
         stage_snap = {n: list(v) for n, v in self.stage_ms.items()}
         agg_snap = dict(self.agg)
         exch_snap = list(self.exch)
-        # a short timed region yields few NVML samples: keep the same load running (untimed) until the
-        # sampler has seen at least 0.4 s of it, so the reported clock is a median under load
-        extra = torch.tensor([1 if (sampler and sampler.in_window() < 24) else 0], device=self.dev)
+        # NVML's clock / power readings lag the load by ~0.1 s: a timed region shorter than 0.6 s is followed by
+        # the same steps (untimed) until the sampler has seen 0.6 s of load, and the reported clock is the
+        # median of the samples taken from 150 ms into that window
+        short = bool(sampler) and (sampler.window[1] - sampler.window[0]) < 0.6
+        extra = torch.tensor([1 if short else 0], device=self.dev)
         if self.distributed:
             dist.broadcast(extra, src=0)
         if int(extra.item()):
-            t_end = time.perf_counter() + 0.4
+            t_end = (sampler.window[0] + 0.6) if sampler else (time.perf_counter() + 0.5)
             while True:
                 self.step()
                 go = torch.tensor([1 if time.perf_counter() < t_end else 0], device=self.dev)
@@ -368,9 +385,12 @@ class ShardedRun:
                 if not int(go.item()):
                     break
             self.torch.cuda.synchronize(self.dev)
+        if sampler:
+            sampler.load_end = time.perf_counter()
         clocks = sampler.stop() if sampler else None
         if clocks is not None and int(extra.item()):
-            clocks["note"] = "timed region shorter than 24 NVML samples: the same steps were repeated (untimed) for 0.4 s while sampling"
+            clocks["note"] = ("timed region shorter than 0.6 s: the same steps were repeated (untimed) until 0.6 s of load had "
+                              "been sampled; sm_mhz = median of the samples from 150 ms into the load")
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev, dtype=torch.float64)
         lt = torch.tensor([launches], device=self.dev, dtype=torch.int64)
         local_ms = statistics.mean(stage_snap["total"]) if stage_snap["total"] else 0.0

@@ -14,7 +14,18 @@ print("exchange", j["exchange"], j["exchange_ms_per_step"], "local", j["local_kn
 print("e2e", {k: j["e2e"][k] for k in ("ms_per_step", "step_ms", "h2d_gb_per_s_per_gpu", "matches_resident_result")})
 print("c3", {k: j["config3"][k] for k in ("ms_per_step", "exchange_ms", "exchange", "frac_of_n_x_burst", "aggregate_tflops", "sampled_queries_equal_fp64_scan", "local_ms_max_over_ranks", "local_ms_min_over_ranks", "fallback_queries_per_step")})
 PY
-TMO=900 run bench_c4_${N}gpu $TR bench.py --gpus $N --workload c4 --steps 2
+CUT=900 run h2d_probe_${N}gpu $TR scripts/h2d_probe.py
+WC=$(python - <<PY
+import json
+try:
+    j = json.loads([l for l in open("gpurun_out/h2d_probe_${N}gpu.log") if l.startswith("{")][-1])
+    print("--c4-host-wc" if j["write_combined"]["gb_per_s_per_gpu_min"] > 1.1 * j["pinned"]["gb_per_s_per_gpu_min"] else "")
+except Exception:
+    print("")
+PY
+)
+echo "c4 host memory flag: [$WC]"
+TMO=900 run bench_c4_${N}gpu $TR bench.py --gpus $N --workload c4 --steps 2 $WC
 python - <<PY
 import json
 j = json.loads([l for l in open("gpurun_out/bench_c4_${N}gpu.log") if l.startswith("{")][-1])
