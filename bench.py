@@ -585,6 +585,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--config4-min-gpus", type=int, default=8, help="run the config-4 leg from this many GPUs on (tests: 2)")
     ap.add_argument("--c4-queries", type=int, default=100_000)
     ap.add_argument("--c4-rows-per-gpu", type=int, default=12_500_000)
     ap.add_argument("--c4-slab-rows", type=int, default=1_000_000)
@@ -663,6 +665,16 @@ def main():
             if distributed:
                 raise
             config3 = {"unavailable": repr(e)[:300]}
+    # BASELINE config 4 (streamed from pinned host memory across 8 B200) rides along in the 8-GPU line
+    config4 = None
+    if n_gpus >= args.config4_min_gpus and distributed and args.workload == "c2" and not args.no_config4:
+        from scripts import bench_c4
+        knn.release_workspace()
+        torch.cuda.empty_cache()
+        c4 = bench_c4.measure(args, n_gpus, world, rank, local_rank, dev, distributed, peaks, ClockSampler, steps=2)
+        if rank == 0 and c4 is not None:
+            config4 = {key: c4.get(key) for key in ("config", "e2e", "resident", "fill_seconds", "clocks", "unavailable")
+                       if c4.get(key) is not None}
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -710,7 +722,7 @@ def main():
                           "mean_rerank_per_query": agg["rerank"] / max(args.steps * nq, 1),
                           "max_candidates": agg["max_candidates"], "max_rerank": agg["max_rerank"],
                           "max_err_over_proven_bound": agg["err_ratio"]},
-            "config3": config3, "gpu_baseline": gpu_baseline}
+            "config3": config3, "config4": config4, "gpu_baseline": gpu_baseline}
     if n_gpus == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(nq, nb_total, d, k, metric, 1, 1)
         line["cpu_baseline"] = {key: cb[key] for key in ("value", "unit", "cores", "kind", "sample")}

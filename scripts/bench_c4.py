@@ -34,11 +34,9 @@ def _mem_available_bytes() -> int:
 
 
 def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
+    """bench.py --workload c4: the whole JSON line is about config 4."""
     import torch
     import torch.distributed as dist
-
-    from neighborhoodwatch_b200 import _native, knn, synth
-    from neighborhoodwatch_b200 import dist as nwdist
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -47,6 +45,22 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
         assert world == n_gpus
+    line = measure(args, n_gpus, world, rank, local_rank, dev, distributed, peaks, ClockSampler,
+                   steps=max(1, min(args.steps, 3)))
+    if rank == 0:
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def measure(args, n_gpus, world, rank, local_rank, dev, distributed, peaks, ClockSampler, steps=2):
+    """Config 4 on the process group that is already up; returns the JSON line (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
+    from neighborhoodwatch_b200 import _native, knn, synth
+    from neighborhoodwatch_b200 import dist as nwdist
+
     nq, rows, slab, d, k, metric = args.c4_queries, args.c4_rows_per_gpu, args.c4_slab_rows, 1024, 100, "sqeuclidean"
     # host memory: every rank pins its whole shard; refuse to drive the box out of memory
     avail = _mem_available_bytes()
@@ -72,11 +86,21 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
 
     t_fill0 = time.perf_counter()
     wc = bool(getattr(args, "c4_host_wc", False))
-    if wc:
-        holder = knn.PinnedArray((rows, d), write_combined=True)
-        base_host = torch.from_numpy(holder.array)
-    else:
-        base_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
+    # every rank pins its shard; if any rank cannot, all of them skip (no rank may be left waiting in a collective)
+    ok, why = 1, ""
+    try:
+        if wc:
+            holder = knn.PinnedArray((rows, d), write_combined=True)
+            base_host = torch.from_numpy(holder.array)
+        else:
+            base_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
+    except Exception as e:  # noqa: BLE001
+        ok, why = 0, repr(e)[:200]
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    if distributed:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return {"unavailable": f"pinned host shard of {rows * d * 4 / 2 ** 30:.1f} GiB per rank could not be allocated {why}"} if rank == 0 else None
     q_host = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
     out_d_host = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
     out_i_host = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
@@ -122,7 +146,6 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    steps = max(1, min(args.steps, 3))
     step_s = []
     launches0 = _native.launch_count()
     for _ in range(steps):
@@ -200,10 +223,11 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
         del base_dev
     except torch.OutOfMemoryError as e:  # noqa: PERF203
         resident = {"unavailable": repr(e)[:200]}
+    del base_host
+    if wc:
+        holder.close()
     if rank != 0:
-        if distributed:
-            dist.destroy_process_group()
-        return
+        return None
 
     flops = 2.0 * nq * nb_total * d
     e2e_value = nq * nb_total / t_med
@@ -243,6 +267,4 @@ def main(args, n_gpus, world, rank, local_rank, peaks, ClockSampler):
         line["value"] = e2e_value
         line["ms_per_step"] = 1e3 * t_med
     line["queries_per_s"] = nq / (line["ms_per_step"] * 1e-3)
-    print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
+    return line
