@@ -226,6 +226,21 @@ int nwk_xchg_merge(nwk_xchg* x, int32_t k_out, float* out_dist, int64_t* out_idx
 int nwk_xchg_check(nwk_xchg* x);
 int nwk_xchg_destroy(nwk_xchg* x);
 
+/* Single-process multi-GPU (SURVEY.md section 8b's nwk_mg_*): one host process, n devices of one box.
+ * Shard i of the base (rows[i] >= k rows, row-major fp32) lives on devices[i]; the queries are HOST memory
+ * and are replicated by the call; ids are global (id_offset + the rows of the shards before).  Each device
+ * runs nwk_knn_f32 on a host thread of its own; device 0 then merges the n lists reading the peers' lists
+ * in place over NVLink (peer access: gather + merge are one kernel) and the [nq, k] result lands in HOST
+ * out_dist / out_idx.  The handle owns its per-device buffers; n * k <= 2048.  Replaces the reference's
+ * temporal batch slicing + CPU merge (cu_knn.py:201-205, merge.py:56-101) for callers without a launcher;
+ * with one process per GPU use nwk_xchg_*. */
+typedef struct nwk_mg nwk_mg;
+int nwk_mg_create(const int32_t* devices, int32_t n, nwk_mg** out);
+int nwk_mg_knn_f32(nwk_mg* mg, const float* const* base_shards, const int64_t* rows, const float* query_host,
+                   int64_t nq, int32_t d, int32_t k, int32_t metric, int64_t id_offset, float* out_dist_host,
+                   int64_t* out_idx_host, uint32_t flags, nwk_knn_stats* stats);
+int nwk_mg_destroy(nwk_mg* mg);
+
 /* Document-level ColBERT MaxSim (the reference's colbert_knn.py:62-126 stops at a
  * token-level kNN over the flattened token embeddings, which nwk_knn_f32 with NWK_METRIC_DOT covers):
  *

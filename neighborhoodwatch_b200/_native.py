@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "nwk_merge_topk_strided", "nwk_merge_topk_ptrs", "nwk_topk_state_reset", "nwk_host_slab_plan", "nwk_host_release",
     "nwk_rows_from_columns_f32", "nwk_xchg_create", "nwk_xchg_handle_bytes", "nwk_xchg_local_handle",
     "nwk_xchg_open_peers", "nwk_xchg_next_slot", "nwk_xchg_merge", "nwk_xchg_check", "nwk_xchg_destroy",
-    "nwk_host_alloc", "nwk_host_free",
+    "nwk_host_alloc", "nwk_host_free", "nwk_mg_create", "nwk_mg_knn_f32", "nwk_mg_destroy",
 )
 
 
@@ -122,6 +122,13 @@ def load() -> ctypes.CDLL:
     lib.nwk_host_alloc.argtypes = [c_size_t, c_int32, POINTER(c_void_p)]
     lib.nwk_host_free.restype = c_int32
     lib.nwk_host_free.argtypes = [c_void_p]
+    lib.nwk_mg_create.restype = c_int32
+    lib.nwk_mg_create.argtypes = [POINTER(c_int32), c_int32, POINTER(c_void_p)]
+    lib.nwk_mg_knn_f32.restype = c_int32
+    lib.nwk_mg_knn_f32.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int64), c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                   c_int64, c_void_p, c_void_p, c_uint32, POINTER(KnnStats)]
+    lib.nwk_mg_destroy.restype = c_int32
+    lib.nwk_mg_destroy.argtypes = [c_void_p]
     lib.nwk_host_release.restype = c_int32
     lib.nwk_host_release.argtypes = []
     lib.nwk_topk_state_create.restype = c_int32

@@ -598,3 +598,163 @@ int nwk_debug_tc_tile(const float* base, int64_t nb, const float* query, int64_t
 }
 
 }  // extern "C"
+
+// ---- single-process multi-GPU ---------------------------------------------------------
+// nwk_mg_*: one host process drives n devices (a host thread per device for the duration of a call).
+// The base is row-sharded: shard i lives on devices[i]; the queries come from host memory and are
+// replicated; every device computes its exact local top-k with global ids; device 0 then merges the n
+// lists reading them straight out of the peers' memory (cudaDeviceEnablePeerAccess: the merge kernel's
+// loads cross NVLink -- gather and merge are one kernel, no staging copy).  The multi-process twin,
+// for one process per GPU, is nwk_xchg_* (nwk_xchg.cu).
+#include <thread>
+#include <vector>
+
+struct nwk_mg {
+  int n = 0;
+  int dev[16] = {};
+  cudaStream_t stream[16] = {};
+  float* query[16] = {};
+  size_t query_bytes[16] = {};
+  char* ws[16] = {};
+  size_t ws_bytes[16] = {};
+  float* out_d[16] = {};
+  size_t out_d_bytes[16] = {};
+  long long* out_i[16] = {};
+  size_t out_i_bytes[16] = {};
+  float* fin_d = nullptr;          // device 0
+  size_t fin_d_bytes = 0;
+  long long* fin_i = nullptr;
+  size_t fin_i_bytes = 0;
+  char* merge_ws = nullptr;
+  size_t merge_ws_bytes = 0;
+};
+
+extern "C" {
+
+int nwk_mg_create(const int32_t* devices, int32_t n, nwk_mg** out) {
+  if (!devices || !out || n < 1 || n > 16) return fail(NWK_ERR_ARG, "nwk_mg_create: 1..16 devices");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  nwk_mg* mg = new nwk_mg();
+  mg->n = n;
+  int rc = NWK_OK;
+  for (int i = 0; i < n && rc == NWK_OK; ++i) {
+    mg->dev[i] = devices[i];
+    if (cudaSetDevice(devices[i]) != cudaSuccess) { rc = fail(NWK_ERR_DEVICE, "cannot select device %d", devices[i]); break; }
+    rc = device_check();
+    if (rc == NWK_OK && cudaStreamCreateWithFlags(&mg->stream[i], cudaStreamNonBlocking) != cudaSuccess)
+      rc = fail(NWK_ERR_CUDA, "stream creation failed on device %d", devices[i]);
+  }
+  // device 0 reads the peers' result lists
+  if (rc == NWK_OK) {
+    cudaSetDevice(devices[0]);
+    for (int i = 1; i < n; ++i) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+      if (!can) { rc = fail(NWK_ERR_DEVICE, "device %d cannot access device %d's memory", devices[0], devices[i]); break; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rc = fail(NWK_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); break; }
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(prev);
+  if (rc != NWK_OK) { nwk_mg_destroy(mg); return rc; }
+  *out = mg;
+  return NWK_OK;
+}
+
+int nwk_mg_knn_f32(nwk_mg* mg, const float* const* base_shards, const int64_t* rows, const float* query_host, int64_t nq,
+                   int32_t d, int32_t k, int32_t metric, int64_t id_offset, float* out_dist_host, int64_t* out_idx_host,
+                   uint32_t flags, nwk_knn_stats* stats) {
+  if (!mg || !base_shards || !rows || !query_host || !out_dist_host || !out_idx_host) return fail(NWK_ERR_ARG, "null pointer argument");
+  if (nq <= 0 || d <= 0 || k <= 0 || k > NWK_MAX_K || (long long)mg->n * k > 2048) return fail(NWK_ERR_ARG, "bad shape");
+  for (int i = 0; i < mg->n; ++i)
+    if (!base_shards[i] || rows[i] < k) return fail(NWK_ERR_ARG, "shard %d: every shard must hold at least k rows", i);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  const int n = mg->n;
+  std::vector<int> rcs(n, NWK_OK);
+  std::vector<std::string> msgs(n);
+  std::vector<nwk_knn_stats> sts(n);
+  std::vector<long long> offs(n, id_offset);
+  for (int i = 1; i < n; ++i) offs[i] = offs[i - 1] + rows[i - 1];
+  const size_t n_out = (size_t)nq * k;
+  auto worker = [&](int i) {
+    auto run = [&]() -> int {
+      NWK_CUDA(cudaSetDevice(mg->dev[i]));
+      NWK_TRY(device_check());
+      const size_t need = nwk_knn_workspace_bytes(rows[i], nq, d, k, metric, flags);
+      NWK_TRY(grow(&mg->query[i], &mg->query_bytes[i], (size_t)nq * d * 4));
+      NWK_TRY(grow(&mg->ws[i], &mg->ws_bytes[i], need));
+      NWK_TRY(grow(&mg->out_d[i], &mg->out_d_bytes[i], n_out * sizeof(float)));
+      NWK_TRY(grow(&mg->out_i[i], &mg->out_i_bytes[i], n_out * sizeof(long long)));
+      NWK_CUDA(cudaMemcpyAsync(mg->query[i], query_host, (size_t)nq * d * 4, cudaMemcpyHostToDevice, mg->stream[i]));
+      NWK_TRY(nwk_knn_f32(base_shards[i], rows[i], mg->query[i], nq, d, k, metric, offs[i], mg->out_d[i],
+                          (int64_t*)mg->out_i[i], mg->ws[i], mg->ws_bytes[i], flags, &sts[i], mg->stream[i]));
+      NWK_CUDA(cudaStreamSynchronize(mg->stream[i]));
+      return NWK_OK;
+    };
+    rcs[i] = run();
+    if (rcs[i] != NWK_OK) msgs[i] = last_error_ref();
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i) th.emplace_back(worker, i);
+  worker(0);
+  for (auto& t : th) t.join();
+  cudaSetDevice(mg->dev[0]);
+  for (int i = 0; i < n; ++i)
+    if (rcs[i] != NWK_OK) { cudaSetDevice(prev); return fail(rcs[i], "device %d: %s", mg->dev[i], msgs[i].c_str()); }
+  int rc = [&]() -> int {
+    const float* dp[16];
+    const long long* ip[16];
+    for (int i = 0; i < n; ++i) { dp[i] = mg->out_d[i]; ip[i] = mg->out_i[i]; }
+    const float* fd = mg->out_d[0];
+    const long long* fi = mg->out_i[0];
+    if (n > 1) {
+      NWK_TRY(grow(&mg->fin_d, &mg->fin_d_bytes, n_out * sizeof(float)));
+      NWK_TRY(grow(&mg->fin_i, &mg->fin_i_bytes, n_out * sizeof(long long)));
+      NWK_TRY(grow(&mg->merge_ws, &mg->merge_ws_bytes, nwk_merge_workspace_bytes(n, nq, k, k)));
+      // gather + merge in one kernel: the lists of devices 1.. are read over NVLink
+      NWK_TRY(merge_topk_ptrs(n, dp, ip, nq, k, k, mg->fin_d, mg->fin_i, mg->merge_ws, mg->merge_ws_bytes, mg->stream[0]));
+      fd = mg->fin_d;
+      fi = mg->fin_i;
+    }
+    NWK_CUDA(cudaMemcpyAsync(out_dist_host, fd, n_out * sizeof(float), cudaMemcpyDeviceToHost, mg->stream[0]));
+    NWK_CUDA(cudaMemcpyAsync(out_idx_host, fi, n_out * sizeof(long long), cudaMemcpyDeviceToHost, mg->stream[0]));
+    NWK_CUDA(cudaStreamSynchronize(mg->stream[0]));
+    return NWK_OK;
+  }();
+  cudaSetDevice(prev);
+  if (rc == NWK_OK && stats) {
+    nwk_knn_stats t = sts[0];
+    for (int i = 1; i < n; ++i) {
+      t.n_fallback_queries += sts[i].n_fallback_queries;
+      t.n_retry_queries += sts[i].n_retry_queries;
+      t.total_candidates += sts[i].total_candidates;
+      t.total_rerank += sts[i].total_rerank;
+      t.gpu_launches += sts[i].gpu_launches;
+      t.max_candidates = std::max(t.max_candidates, sts[i].max_candidates);
+      t.max_rerank = std::max(t.max_rerank, sts[i].max_rerank);
+      t.max_err_ratio = std::max(t.max_err_ratio, sts[i].max_err_ratio);
+    }
+    *stats = t;
+  }
+  return rc;
+}
+
+int nwk_mg_destroy(nwk_mg* mg) {
+  if (!mg) return NWK_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int i = 0; i < mg->n; ++i) {
+    if (cudaSetDevice(mg->dev[i]) != cudaSuccess) continue;
+    if (mg->stream[i]) { cudaStreamSynchronize(mg->stream[i]); cudaStreamDestroy(mg->stream[i]); }
+    cudaFree(mg->query[i]); cudaFree(mg->ws[i]); cudaFree(mg->out_d[i]); cudaFree(mg->out_i[i]);
+    if (i == 0) { cudaFree(mg->fin_d); cudaFree(mg->fin_i); cudaFree(mg->merge_ws); }
+  }
+  cudaSetDevice(prev);
+  delete mg;
+  return NWK_OK;
+}
+
+}  // extern "C"

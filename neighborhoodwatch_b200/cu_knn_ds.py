@@ -87,10 +87,24 @@ def tune_memory(dataset, batch_size, max_memory_threshold, rmm=None, column_name
         return int(0.8 * batch_size)
 
 
+def _fragment_rows(piece) -> int:
+    """Rows of a (row-group) fragment from the parquet metadata; ``count_rows()`` of a fragment made by
+    ``split_by_row_group`` answers for the whole file."""
+    try:
+        piece.ensure_complete_metadata()
+        return int(sum(rg.num_rows for rg in piece.row_groups))
+    except Exception:  # noqa: BLE001 -- not a parquet fragment
+        return int(piece.count_rows())
+
+
 def _iter_record_batches(dataset, columns: List[str], start: int, stop: int, batch_rows: int) -> Iterator[pa.RecordBatch]:
     """Record batches covering rows ``[start, stop)`` of the dataset, in order.  Row groups that lie
     wholly before ``start`` are skipped on their metadata (never decoded): a rank of a multi-GPU run
-    pays for its own shard only."""
+    pays for its own shard only.  A row group is decoded in one call (arrow decodes its columns in
+    parallel: one column per dimension gives it hundreds to work on) and the next two row groups are
+    decoded ahead on helper threads while the caller packs the current one."""
+    from concurrent.futures import ThreadPoolExecutor
+    todo = []                                        # (piece, first row of the piece)
     pos = 0
     for frag in dataset.get_fragments():
         try:
@@ -99,19 +113,27 @@ def _iter_record_batches(dataset, columns: List[str], start: int, stop: int, bat
             pieces = [frag]
         for piece in pieces:
             if pos >= stop:
-                return
-            n = piece.count_rows()
-            if pos + n <= start:
-                pos += n
+                break
+            n = _fragment_rows(piece)
+            if pos + n > start:
+                todo.append((piece, pos))
+            pos += n
+        if pos >= stop:
+            break
+    if not todo:
+        return
+    with ThreadPoolExecutor(max_workers=2) as ahead:
+        pending = [ahead.submit(piece.to_table, columns=columns) for piece, _ in todo[:2]]
+        for i, (piece, p0) in enumerate(todo):
+            table = pending.pop(0).result()
+            if i + 2 < len(todo):
+                pending.append(ahead.submit(todo[i + 2][0].to_table, columns=columns))
+            lo, hi = max(p0, start), min(p0 + table.num_rows, stop)
+            if hi <= lo:
                 continue
-            for batch in piece.to_batches(columns=columns, batch_size=batch_rows):
-                b0 = pos
-                pos += len(batch)
-                lo, hi = max(b0, start), min(pos, stop)
-                if hi > lo:
-                    yield batch.slice(lo - b0, hi - lo)
-                if pos >= stop:
-                    return
+            for batch in table.slice(lo - p0, hi - lo).to_batches(max_chunksize=batch_rows):
+                if len(batch):
+                    yield batch
 
 
 def _iter_slabs(dataset, columns: List[str], limit: int, slab_rows: int, start: int = 0,
@@ -144,14 +166,47 @@ def _iter_slabs(dataset, columns: List[str], limit: int, slab_rows: int, start: 
         yield off, have, pending
 
 
+_pack_pool = None
+
+
+def _pool():
+    """A small thread pool for packing decoded columns into pinned staging (numpy's contiguous copies
+    release the GIL; arrow -> numpy is zero-copy for float32 columns without nulls)."""
+    global _pack_pool
+    if _pack_pool is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 4
+        _pack_pool = ThreadPoolExecutor(max_workers=max(2, min(16, cores // 2)))
+    return _pack_pool
+
+
 def _fill_pinned(staging: np.ndarray, batches: List[pa.RecordBatch], columns: List[str]) -> None:
     """Column-per-dimension record batches -> column-major ``[d, rows]`` pinned staging."""
+    jobs = []
     off = 0
     for b in batches:
         n = len(b)
-        for j, name in enumerate(columns):
-            staging[j, off:off + n] = b.column(b.schema.get_field_index(name)).to_numpy(zero_copy_only=False)
+        if n:
+            idx = [b.schema.get_field_index(name) for name in columns]
+            for j0 in range(0, len(columns), 64):
+                jobs.append((b, idx, j0, min(j0 + 64, len(columns)), off, n))
         off += n
+
+    def pack(job):
+        b, idx, j0, j1, o, n = job
+        for j in range(j0, j1):
+            staging[j, o:o + n] = b.column(idx[j]).to_numpy(zero_copy_only=False)
+
+    total = sum(job[5] * (job[3] - job[2]) for job in jobs)
+    if total >= (1 << 22) and len(jobs) > 1:
+        list(_pool().map(pack, jobs))
+    else:
+        for job in jobs:
+            pack(job)
 
 
 def compute_knn_ds(data_dir,

@@ -244,6 +244,53 @@ class RunningTopK:
             pass
 
 
+class MultiGpu:
+    """Single-process multi-GPU exact kNN (``nwk_mg_*``): base shards resident on several devices of this
+    process, queries from host memory, the global ``[nq, k]`` result back in host memory."""
+
+    def __init__(self, devices):
+        self._lib = _native.load()
+        self.devices = [int(x) for x in devices]
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._h = ctypes.c_void_p()
+        _native.check(self._lib.nwk_mg_create(arr, len(self.devices), ctypes.byref(self._h)))
+
+    def knn(self, base_shards, queries, k: int, metric: str = "sqeuclidean", id_offset: int = 0):
+        global last_stats
+        import numpy as np
+        assert len(base_shards) == len(self.devices)
+        shards = []
+        for dev, b in zip(self.devices, base_shards):
+            assert b.device.type == "cuda" and b.device.index == dev and b.dtype == torch.float32 and b.is_contiguous()
+            shards.append(b)
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, d = q.shape
+        assert all(b.shape[1] == d for b in shards)
+        assert all(k <= b.shape[0] for b in shards), "every shard must hold at least k rows"      # cu_knn.py:237 per shard
+        ptrs = (ctypes.c_void_p * len(shards))(*[b.data_ptr() for b in shards])
+        rows = (ctypes.c_int64 * len(shards))(*[b.shape[0] for b in shards])
+        out_d = np.empty((nq, k), dtype=np.float32)
+        out_i = np.empty((nq, k), dtype=np.int64)
+        stats = _native.KnnStats()
+        for b in shards:
+            torch.cuda.current_stream(b.device).synchronize()      # the shards are complete before the library's streams read them
+        _native.check(self._lib.nwk_mg_knn_f32(self._h, ptrs, rows, q.ctypes.data, nq, d, k, _native.METRIC_IDS[metric],
+                                               int(id_offset), out_d.ctypes.data, out_i.ctypes.data, 0, ctypes.byref(stats)))
+        last_stats = stats.as_dict()
+        return out_d, out_i
+
+    def close(self):
+        if self._h:
+            self._lib.nwk_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class PinnedArray:
     """``[rows, d]`` fp32 pinned host memory from ``nwk_host_alloc`` (optionally write-combined), exposed as a
     numpy array (``.array``); freed with the object."""

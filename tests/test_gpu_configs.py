@@ -256,3 +256,23 @@ def test_entry_points_are_rank_aware_world2(tmp_path):
         f_i = read(get_partial_indices_filename(str(tmp_path / sub), -1), np.int64)
         np.testing.assert_array_equal(f_i, t_i, err_msg=sub)
         np.testing.assert_allclose(f_d, t_d, rtol=1e-5, atol=1e-6, err_msg=sub)
+
+
+def test_single_process_multi_gpu(cuda_device):
+    """nwk_mg_*: one process, two devices, shards of unequal size; device 0 merges the peers' lists in place over
+    NVLink.  Equal to the oracle over the whole base, twice (the handle's buffers are reused)."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nq, nb, d, k = 300, 120_001, 256, 100
+    base, q = synth.vectors(nb, d, 1234), synth.vectors(nq, d, 5678)
+    cut = 70_000
+    shards = [torch.from_numpy(base[:cut]).to("cuda:0"), torch.from_numpy(base[cut:]).to("cuda:1")]
+    mg = knn.MultiGpu([0, 1])
+    for metric in ("sqeuclidean", "cosine"):
+        got_d, got_i = mg.knn(shards, q, k, metric=metric, id_offset=7)
+        _check(got_d, got_i, base, q, k, metric, id_offset=7)
+    mg.close()
+    with pytest.raises(Exception):
+        knn.MultiGpu([0, 1]).knn([shards[0][:50], shards[1]], q, k)      # a shard shorter than k
