@@ -277,8 +277,20 @@ __device__ __forceinline__ double ms_error_bound(const Scalars* sc, float c_rel,
          Tq * ldexp(1.0, -25 - sq) * sqrt((double)d) * dmax + 1e-30;
 }
 
+// float -> double is exact, so it can be done on the integer pipe: F2F.F64.F32 shares the fp64 pipe with
+// the DFMAs and costs about four of them (measured: a variant with twice the conversions per DFMA and
+// half the shared-memory loads ran 1.33 x slower, 33.6 -> 44.3 ms), while three integer instructions
+// overlap with them.  Zeros, denormals, inf and nan take the conversion instruction.
+__device__ __forceinline__ double f2d_exact(float f) {
+  const uint32_t b = __float_as_uint(f);
+  const uint32_t a = b & 0x7fffffffu;
+  if (a - 0x00800000u < 0x7f000000u)                     // a normal number
+    return __hiloint2double((int)((b & 0x80000000u) | ((a >> 3) + 0x38000000u)), (int)(b << 29));
+  return (double)f;
+}
+
 // exact fp64 MaxSim of (query, document) pairs: grid (pairs per query, queries); lane = query token,
-// warp = document tokens j = warp, warp + 8, ... of a tile.
+// warp = document tokens j = warp, warp + 4, ... of a tile.
 struct MsExact {
   const float* qtok; const float* docs; const int* doc_len;
   long long nq, nd; int Tq, Td, d;
@@ -288,18 +300,30 @@ struct MsExact {
   double* out;                // [.][nc]  -(exact score)
   // candidates only: a document whose approximate key lies more than 2 E_q above the k-th best cannot be
   // among the true top k and is not scored (its slot gets +inf)
-  const float* cand_key; int k; const Scalars* sc; float c_rel;
+  const float* cand_key; int k;
+  const float* eq;            // [.] E_q of the (selected) queries (ms_eq_kernel)
 };
 
-// The document is staged tile by tile (tj tokens) in shared memory as doubles, converted once for all
-// query tokens; lane = query token keeps 8 of its components as doubles in registers per pass and
-// one accumulator per document token of its warp (tj / 8 of them), so the inner loop is one
-// broadcast LDS.128 per two DFMAs and no conversions.
-__global__ void __launch_bounds__(256)
-ms_exact_kernel(const MsExact a, const int tj) {
+// The document is staged tile by tile (TJ = 4 PW tokens) in shared memory as doubles, converted once for
+// all query tokens; lane = query token keeps 8 of its components as doubles in registers per pass and
+// one accumulator per document token of its warp (PW of them: tokens warp, warp + 4, ...).  The inner
+// loop is straight-line: 4 broadcast LDS.128 + 8 DFMA per document token, no branches (the tokens past
+// the end of the document are staged as zeros and left out of the maximum afterwards).
+// Round 2 rebalanced it around the fp64 pipe (one DFMA per two clocks and scheduler): the first version
+// (8 warps, 8 tokens per warp, F2F conversions, a validity branch per token) spent a third of that
+// pipe on the conversions of the query components and about as many issue slots on loop overhead as
+// on DFMAs (27 % of the pipe's rate).  Now the conversions run on the integer pipe (f2d_exact) and
+// are amortised over 16 document tokens per lane, 128-thread CTAs keep three CTAs per SM.
+constexpr int MSX_THREADS = 128;
+constexpr int MSX_WARPS = MSX_THREADS / 32;
+
+template <int PW>
+__global__ void __launch_bounds__(MSX_THREADS)
+ms_exact_kernel(const MsExact a) {
+  constexpr int TJ = PW * MSX_WARPS;
   extern __shared__ __align__(16) unsigned char msx_smem[];
-  double* s_doc = reinterpret_cast<double*>(msx_smem);                  // [tj][d]
-  double* s_max = s_doc + (size_t)tj * a.d;                             // [8][Tq]
+  double* s_doc = reinterpret_cast<double*>(msx_smem);                  // [TJ][d]
+  double* s_max = s_doc + (size_t)TJ * a.d;                             // [MSX_WARPS][Tq]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long f = blockIdx.y;
   const long long q = a.qsel ? a.qsel[f] : f;
@@ -313,77 +337,80 @@ ms_exact_kernel(const MsExact a, const int tj) {
   const float* qrow0 = a.qtok + q * a.Tq * a.d;
   const int valid = a.doc_len ? max(0, min(a.doc_len[doc], a.Td)) : a.Td;
   if (a.cand_key) {
-    // sum_t |q_t| (warp w: tokens w, w + 8, ...), then the band test
-    double sn = 0.0;
-    for (int t = warp; t < a.Tq; t += 8) {
-      float n2 = 0.f;
-      for (int c = lane; c < a.d; c += 32) { const float v = qrow0[t * a.d + c]; n2 = fmaf(v, v, n2); }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-      sn += sqrt((double)n2);
-    }
-    if (lane == 0) s_max[warp] = sn;
-    __syncthreads();
-    double sum_norm = 0.0;
-    for (int w = 0; w < 8; ++w) sum_norm += s_max[w];
-    const double E = ms_error_bound(a.sc, a.c_rel, a.Tq, a.d, sum_norm * 1.000001);
+    // the band test first (two loads): most candidates of a query end here
     const int kk = (int)min((long long)a.k, a.nc);
-    const bool skip = (double)a.cand_key[f * a.nc + slot] > (double)a.cand_key[f * a.nc + kk - 1] + 2.0 * E;
-    __syncthreads();                               // s_max is reused below
-    if (skip) {
+    const double E = (double)a.eq[f];
+    if ((double)a.cand_key[f * a.nc + slot] > (double)a.cand_key[f * a.nc + kk - 1] + 2.0 * E) {
       if (threadIdx.x == 0) a.out[f * a.nc + slot] = -NINF;
       return;
     }
   }
   constexpr int MAXG = 4;                          // Tq <= 128: up to four tokens per lane
   const int groups = (a.Tq + 31) / 32;
-  const int per_warp = tj / 8;                     // document tokens of a tile per warp (<= 8)
+  const int d4 = a.d >> 2;
   double best[MAXG];
 #pragma unroll
   for (int g = 0; g < MAXG; ++g) best[g] = NINF;
-  for (int tile0 = 0; tile0 < valid; tile0 += tj) {
-    const int nt = min(tj, valid - tile0);
+  for (int tile0 = 0; tile0 < valid; tile0 += TJ) {
+    const int nt = min(TJ, valid - tile0);
     __syncthreads();
-    for (int e = threadIdx.x; e < nt * a.d; e += blockDim.x)
-      s_doc[e] = (double)a.docs[(doc * a.Td + tile0) * a.d + e];
+    // stage the tile: a warp converts one token per trip (float4 reads, 16-byte stores of doubles)
+#pragma unroll 1
+    for (int j = warp; j < TJ; j += MSX_WARPS) {
+      const float4* src = reinterpret_cast<const float4*>(a.docs + (doc * a.Td + tile0 + j) * a.d);
+      double* dst = s_doc + (size_t)j * a.d;
+      for (int c4 = lane; c4 < d4; c4 += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nt) v = __ldg(src + c4);
+        *reinterpret_cast<double2*>(dst + 4 * c4) = make_double2(f2d_exact(v.x), f2d_exact(v.y));
+        *reinterpret_cast<double2*>(dst + 4 * c4 + 2) = make_double2(f2d_exact(v.z), f2d_exact(v.w));
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int g = 0; g < MAXG; ++g) {
       if (g >= groups) break;
       const int t = g * 32 + lane;
       const float* qrow = qrow0 + (long long)min(t, a.Tq - 1) * a.d;
-      double acc[8];
+      double acc[PW];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
-      for (int cb = 0; cb < a.d; cb += 8) {
-        double q8[8];
-        const float4 qa = *reinterpret_cast<const float4*>(qrow + cb);
-        float4 qb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cb + 4 < a.d) qb = *reinterpret_cast<const float4*>(qrow + cb + 4);
-        q8[0] = qa.x; q8[1] = qa.y; q8[2] = qa.z; q8[3] = qa.w; q8[4] = qb.x; q8[5] = qb.y; q8[6] = qb.z; q8[7] = qb.w;
-        const int nc8 = min(8, a.d - cb);
+      for (int jj = 0; jj < PW; ++jj) acc[jj] = 0.0;
+      const double* dbase = s_doc + (size_t)warp * a.d;
+      const int dstep = MSX_WARPS * a.d;           // doubles between two tokens of this warp
+      int cb = 0;
+#pragma unroll 1
+      for (; cb + 8 <= a.d; cb += 8) {
+        const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow + cb));
+        const float4 qb = __ldg(reinterpret_cast<const float4*>(qrow + cb + 4));
+        const double q0 = f2d_exact(qa.x), q1 = f2d_exact(qa.y), q2 = f2d_exact(qa.z), q3 = f2d_exact(qa.w);
+        const double q4 = f2d_exact(qb.x), q5 = f2d_exact(qb.y), q6 = f2d_exact(qb.z), q7 = f2d_exact(qb.w);
+        const double2* dv = reinterpret_cast<const double2*>(dbase + cb);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          if (jj >= per_warp) break;
-          const int j = warp + 8 * jj;                 // token inside the tile (warp-uniform)
-          if (j < nt) {
-            const double* dv = s_doc + (size_t)j * a.d + cb;
-            if (nc8 == 8) {
+        for (int jj = 0; jj < PW; ++jj) {
+          const double2 d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3];
+          double x = acc[jj];
+          x = fma(q0, d0.x, x); x = fma(q1, d0.y, x); x = fma(q2, d1.x, x); x = fma(q3, d1.y, x);
+          x = fma(q4, d2.x, x); x = fma(q5, d2.y, x); x = fma(q6, d3.x, x); x = fma(q7, d3.y, x);
+          acc[jj] = x;
+          dv += dstep / 2;
+        }
+      }
+      if (cb < a.d) {                              // d % 8 == 4: the last four components
+        const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow + cb));
+        const double q0 = f2d_exact(qa.x), q1 = f2d_exact(qa.y), q2 = f2d_exact(qa.z), q3 = f2d_exact(qa.w);
+        const double2* dv = reinterpret_cast<const double2*>(dbase + cb);
 #pragma unroll
-              for (int c = 0; c < 8; c += 2) {
-                const double2 d2 = *reinterpret_cast<const double2*>(dv + c);
-                acc[jj] = fma(q8[c], d2.x, acc[jj]);
-                acc[jj] = fma(q8[c + 1], d2.y, acc[jj]);
-              }
-            } else {
-              for (int c = 0; c < nc8; ++c) acc[jj] = fma(q8[c], dv[c], acc[jj]);
-            }
-          }
+        for (int jj = 0; jj < PW; ++jj) {
+          const double2 d0 = dv[0], d1 = dv[1];
+          double x = acc[jj];
+          x = fma(q0, d0.x, x); x = fma(q1, d0.y, x); x = fma(q2, d1.x, x); x = fma(q3, d1.y, x);
+          acc[jj] = x;
+          dv += dstep / 2;
         }
       }
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj)
-        if (jj < per_warp && warp + 8 * jj < nt) best[g] = fmax(best[g], acc[jj]);
+      for (int jj = 0; jj < PW; ++jj)
+        if (warp + MSX_WARPS * jj < nt) best[g] = fmax(best[g], acc[jj]);
     }
   }
   __syncthreads();
@@ -397,12 +424,32 @@ ms_exact_kernel(const MsExact a, const int tj) {
     double sum = 0.0;
     for (int t = lane; t < a.Tq; t += 32) {
       double b = s_max[t];
-      for (int w = 1; w < 8; ++w) b = fmax(b, s_max[w * a.Tq + t]);
+      for (int w = 1; w < MSX_WARPS; ++w) b = fmax(b, s_max[w * a.Tq + t]);
       sum += b;
     }
     sum = warp_sum(sum);
     if (lane == 0) a.out[f * a.nc + slot] = -sum;
   }
+}
+
+// E_q of every query (ms_error_bound of sum_t |q_t|), once per call: the band test of ms_exact_kernel and
+// the certificate of ms_final_kernel read it.  One warp per query.
+__global__ void __launch_bounds__(256)
+ms_eq_kernel(const float* __restrict__ qtok, long long nq, int Tq, int d, const Scalars* __restrict__ sc, float c_rel,
+             float* __restrict__ eq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 8 + warp;
+  if (q >= nq) return;
+  double sn = 0.0;
+  for (int t = 0; t < Tq; ++t) {
+    float n2 = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = qtok[(q * Tq + t) * d + c]; n2 = fmaf(v, v, n2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    sn += sqrt((double)n2);
+  }
+  // (rounded up: the bound must not shrink in the fp32 store)
+  if (lane == 0) eq[q] = __double2float_ru(ms_error_bound(sc, c_rel, Tq, d, sn * 1.000001));
 }
 
 // per query: order the candidates by (exact score descending, document id), emit k, certify
@@ -530,7 +577,7 @@ size_t maxsim_workspace_bytes(long long nq, int Tq, long long nd, int Td, int d,
   b += align_up((size_t)nd * pl.N * pl.pitch * 2, 256);
   b += align_up((size_t)nq * nd * 8, 256);
   b += align_up((size_t)nq * pl.nc * 4, 256) + align_up((size_t)nq * pl.nc * 8, 256) * 2;
-  b += align_up((size_t)nq * 4, 256) + 4096;
+  b += align_up((size_t)nq * 4, 256) * 2 + 4096;
   b += align_up((size_t)pl.fb_rows * nd * 8, 256);
   const size_t t1 = topk_from_keys_workspace_bytes(nd, nq, (int)pl.nc), t2 = topk_from_keys_workspace_bytes(nd, pl.fb_rows, k);
   b += (t1 > t2 ? t1 : t2) + 4096;
@@ -553,6 +600,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   long long* cand_id = ar.take<long long>((size_t)nq * pl.nc);
   double* exact = ar.take<double>((size_t)nq * pl.nc);
   int* fail_list = ar.take<int>((size_t)nq);
+  float* eq = ar.take<float>((size_t)nq);
   Scalars* sc = ar.take<Scalars>(1);
   double* fb = ar.take<double>((size_t)pl.fb_rows * nd);
   ar.off = align_up(ar.off, 256);
@@ -598,24 +646,36 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   NWK_TRY(topk_from_keys(neg, nd, nd, nq, (int)pl.nc, nullptr, 0, cand_key, cand_id, tws, tws_bytes, s));
   cudaEventRecord(ev[3], s);
 
-  // document tile of the exact kernel: tj tokens as doubles, about 64 KB
-  int tj = (64 * 1024 / (d * 8)) / 8 * 8;
-  tj = tj < 8 ? 8 : (tj > 64 ? 64 : tj);
-  const int ex_smem = tj * d * 8 + 8 * Tq * 8 + 64;
+  // document tile of the exact kernel: TJ = 4 PW tokens as doubles, at most 64 KB (three CTAs per SM)
+  int pw = 16;
+  while (pw > 2 && (size_t)pw * MSX_WARPS * d * 8 > 64 * 1024) pw >>= 1;
+  const int ex_smem = pw * MSX_WARPS * d * 8 + MSX_WARPS * Tq * 8 + 64;
   if (ex_smem > dev_state()->ms_ex_optin) {
-    NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
+    NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
+    NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
+    NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
+    NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
     dev_state()->ms_ex_optin = ex_smem;
   }
+  auto launch_exact = [&](const MsExact& es, dim3 grid) -> int {
+    if (pw == 16) ms_exact_kernel<16><<<grid, MSX_THREADS, ex_smem, s>>>(es);
+    else if (pw == 8) ms_exact_kernel<8><<<grid, MSX_THREADS, ex_smem, s>>>(es);
+    else if (pw == 4) ms_exact_kernel<4><<<grid, MSX_THREADS, ex_smem, s>>>(es);
+    else ms_exact_kernel<2><<<grid, MSX_THREADS, ex_smem, s>>>(es);
+    NWK_LAUNCH_CHECK();
+    return NWK_OK;
+  };
   const float c_rel = (float)(1.0 / 1024.0 * 1.001 + ((double)d / 16.0 + 2.0) / 4194304.0);
+  ms_eq_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(qtok, nq, Tq, d, sc, c_rel, eq);
+  NWK_LAUNCH_CHECK();
   MsExact e{};
   e.qtok = qtok; e.docs = docs; e.doc_len = doc_len; e.nq = nq; e.nd = nd; e.Tq = Tq; e.Td = Td; e.d = d;
   for (long long q0 = 0; q0 < nq; q0 += 32768) {
     const long long nf = std::min<long long>(32768, nq - q0);
     MsExact es = e;
     es.qtok = qtok + q0 * Tq * d; es.cand = cand_id + q0 * pl.nc; es.nc = pl.nc; es.out = exact + q0 * pl.nc;
-    es.cand_key = cand_key + q0 * pl.nc; es.k = k; es.sc = sc; es.c_rel = c_rel;
-    ms_exact_kernel<<<dim3((unsigned)pl.nc, (unsigned)nf), 256, ex_smem, s>>>(es, tj);
-    NWK_LAUNCH_CHECK();
+    es.cand_key = cand_key + q0 * pl.nc; es.k = k; es.eq = eq + q0;
+    NWK_TRY(launch_exact(es, dim3((unsigned)pl.nc, (unsigned)nf)));
   }
   MsFinal f{};
   f.qtok = qtok; f.nq = nq; f.Tq = Tq; f.d = d; f.k = k; f.nc = pl.nc; f.nd = nd; f.cand_key = cand_key; f.cand_id = cand_id;
@@ -638,8 +698,7 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
     const long long nf = std::min<long long>(pl.fb_rows, h.fail_cnt - done);
     MsExact es = e;
     es.qsel = fail_list + done; es.cand = nullptr; es.nc = nd; es.out = fb;
-    ms_exact_kernel<<<dim3((unsigned)nd, (unsigned)nf), 256, ex_smem, s>>>(es, tj);
-    NWK_LAUNCH_CHECK();
+    NWK_TRY(launch_exact(es, dim3((unsigned)nd, (unsigned)nf)));
     NWK_TRY(topk_from_keys(fb, nd, nd, nf, k, fail_list + done, id_offset, out_score, out_idx, tws, tws_bytes, s));
     ms_negate_rows_kernel<<<(unsigned)((nf * k + 255) / 256), 256, 0, s>>>(out_score, fail_list + done, (int)nf, k);
     NWK_LAUNCH_CHECK();

@@ -98,3 +98,33 @@ def test_colbert_token_knn(tmp_path, cuda_device):
     f_i, _ = read_matrix(get_partial_indices_filename(data_dir, -1), np.int64)
     t_d, t_i = ko.knn_f64(base, q, k, "dot")
     np.testing.assert_array_equal(f_i, t_i)
+
+
+@pytest.mark.parametrize("rows,d,ld_extra,shift", [
+    (1000, 384, 0, 0),        # both sides vectorised (16-byte aligned, ld % 4 == 0, d % 4 == 0)
+    (1000, 384, 24, 0),       # staging wider than the rows in use (the streaming driver's slabs)
+    (257, 100, 0, 0),         # ld % 4 != 0: scalar reads, float4 writes
+    (1001, 130, 3, 0),        # d % 4 != 0: float4 reads, scalar writes
+    (63, 7, 0, 0),            # smaller than a tile on both sides
+    (4100, 65, 0, 1),         # source 4 bytes off a 16-byte boundary
+    (130, 1, 0, 0),
+])
+def test_rows_from_columns_shapes(cuda_device, rows, d, ld_extra, shift):
+    """nwk_rows_from_columns_f32 (the reference's cupy.copy(order='C'), cu_knn.py:211,235) on ragged shapes:
+    every combination of vectorised / scalar sides and partial tiles, bit-exact against numpy's transpose."""
+    import torch
+    from neighborhoodwatch_b200 import knn
+    rng = np.random.default_rng(rows * 131 + d)
+    ld = rows + ld_extra
+    host = rng.standard_normal((d, ld)).astype(np.float32)
+    flat = torch.empty(d * ld + 4, dtype=torch.float32, device=cuda_device)
+    cols = flat[shift:shift + d * ld].view(d, ld)
+    cols.copy_(torch.from_numpy(host))
+    out = knn.rows_from_columns(cols, rows)
+    assert out.shape == (rows, d)
+    assert np.array_equal(out.cpu().numpy(), host[:, :rows].T)
+    # into a caller's larger buffer: rows beyond `rows` stay untouched
+    buf = torch.full((rows + 5, d), -7.0, dtype=torch.float32, device=cuda_device)
+    got = knn.rows_from_columns(cols, rows, out=buf)
+    assert np.array_equal(got.cpu().numpy(), host[:, :rows].T)
+    assert bool((buf[rows:] == -7.0).all())
