@@ -277,18 +277,6 @@ __device__ __forceinline__ double ms_error_bound(const Scalars* sc, float c_rel,
          Tq * ldexp(1.0, -25 - sq) * sqrt((double)d) * dmax + 1e-30;
 }
 
-// float -> double is exact, so it can be done on the integer pipe: F2F.F64.F32 shares the fp64 pipe with
-// the DFMAs and costs about four of them (measured: a variant with twice the conversions per DFMA and
-// half the shared-memory loads ran 1.33 x slower, 33.6 -> 44.3 ms), while three integer instructions
-// overlap with them.  Zeros, denormals, inf and nan take the conversion instruction.
-__device__ __forceinline__ double f2d_exact(float f) {
-  const uint32_t b = __float_as_uint(f);
-  const uint32_t a = b & 0x7fffffffu;
-  if (a - 0x00800000u < 0x7f000000u)                     // a normal number
-    return __hiloint2double((int)((b & 0x80000000u) | ((a >> 3) + 0x38000000u)), (int)(b << 29));
-  return (double)f;
-}
-
 // exact fp64 MaxSim of (query, document) pairs: grid (pairs per query, queries); lane = query token,
 // warp = document tokens j = warp, warp + 4, ... of a tile.
 struct MsExact {

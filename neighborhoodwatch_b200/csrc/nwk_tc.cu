@@ -1405,6 +1405,9 @@ rerank_kernel(const FinParams p) {
 #pragma unroll
       for (int r = 0; r < RR_ROWS; ++r) {
         // same operation order as scan_dist_kernel: both exact paths agree bit for bit
+        // (the conversions stay F2F here: moving them to the integer pipe with f2d_exact, which pays in the
+        //  DFMA-bound MaxSim re-scoring, made this HBM-gather-bound kernel slower -- finish 17.8 -> 20.8 ms on a
+        //  config-4 slab, 1.49 -> 1.59 ms at config 2)
         const double b0 = b4[r].x, b1 = b4[r].y, b2 = b4[r].z, b3 = b4[r].w;
         if (p.metric == NWK_METRIC_COSINE) {
           bn2[r] = fma(b0, b0, bn2[r]); bn2[r] = fma(b1, b1, bn2[r]);
