@@ -366,10 +366,20 @@ ms_exact_kernel(const MsExact a) {
       const double* dbase = s_doc + (size_t)warp * a.d;
       const int dstep = MSX_WARPS * a.d;           // doubles between two tokens of this warp
       int cb = 0;
+      // (the query components of the next pass are fetched a pass ahead: a lane reads its own token's row,
+      //  32 bytes per pass, and the L1 round trip was the kernel's first stall reason)
+      float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+      if (a.d >= 8) {
+        qa = __ldg(reinterpret_cast<const float4*>(qrow));
+        qb = __ldg(reinterpret_cast<const float4*>(qrow + 4));
+      }
 #pragma unroll 1
       for (; cb + 8 <= a.d; cb += 8) {
-        const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow + cb));
-        const float4 qb = __ldg(reinterpret_cast<const float4*>(qrow + cb + 4));
+        float4 na = qa, nb = qb;
+        if (cb + 16 <= a.d) {
+          na = __ldg(reinterpret_cast<const float4*>(qrow + cb + 8));
+          nb = __ldg(reinterpret_cast<const float4*>(qrow + cb + 12));
+        }
         const double q0 = f2d_exact(qa.x), q1 = f2d_exact(qa.y), q2 = f2d_exact(qa.z), q3 = f2d_exact(qa.w);
         const double q4 = f2d_exact(qb.x), q5 = f2d_exact(qb.y), q6 = f2d_exact(qb.z), q7 = f2d_exact(qb.w);
         const double2* dv = reinterpret_cast<const double2*>(dbase + cb);
@@ -382,6 +392,7 @@ ms_exact_kernel(const MsExact a) {
           acc[jj] = x;
           dv += dstep / 2;
         }
+        qa = na; qb = nb;
       }
       if (cb < a.d) {                              // d % 8 == 4: the last four components
         const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow + cb));

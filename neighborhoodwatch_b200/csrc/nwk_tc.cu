@@ -277,13 +277,16 @@ struct SampleOut {
 //   sample   (so.stride_log2 >= 0): only the stratified sample rows (one per block of 2^stride_log2
 //            rows) -> the compact sample matrix with its own alpha / beta, which the sample pass needs
 //            before any threshold exists.  Reads 1/32 .. 1/64 of the base.
-template <bool F16>
-__global__ void __launch_bounds__(256)
+// ROW_CACHE = float4 per lane kept in registers (8: rows up to 1024 columns are read once; longer rows re-read
+// their tail).  Short rows (d <= 256) take the ROW_CACHE = 2 instantiation: half the registers, twice the
+// warps per SM -- a warp has one 512-byte row in flight at d = 128, so the resident warps are the HBM
+// parallelism of that shape.
+template <bool F16, int ROW_CACHE = 8>
+__global__ void __launch_bounds__(256, ROW_CACHE <= 2 ? 6 : 1)
 baseprep_kernel(const float* __restrict__ base, long long nb, long long row_begin, long long row_end, int d, int dh,
                 int metric, float* __restrict__ alpha, float* __restrict__ beta, Scalars* __restrict__ sc,
                 __half* __restrict__ bh, const SampleOut so, const int direct, const int pitch) {
   // pitch = elements per row of the fp16 copies: dh, or dh + L2X_COLS for direct squared-L2 keys
-  constexpr int ROW_CACHE = 8;
   const bool sample_mode = so.stride_log2 >= 0;
   if (sample_mode) {
     const float PINF = __int_as_float(0x7f800000);
@@ -321,6 +324,9 @@ baseprep_kernel(const float* __restrict__ base, long long nb, long long row_begi
     float mx = 0.f;
 #pragma unroll
     for (int i = 0; i < ROW_CACHE; ++i) {
+      // (warp-uniform: short rows skip the empty part of the cache -- its conversions and DFMAs on zeros kept
+      //  the fp64 pipe busy for 8 x 128 columns whatever d was: 1.17 ms for 2.25M rows of d = 128, 1.5 TB/s)
+      if (i * 128 >= d) break;
       const float4 v = cache[i];
       a = fma((double)v.x, (double)v.x, a);
       a = fma((double)v.y, (double)v.y, a);
@@ -1916,7 +1922,8 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     so.ns = pl.ns; so.ns_pad = pl.ns_pad;
     so.rows = srows; so.alpha = salpha; so.beta = sbeta;
     long long blocks = std::min<long long>((pl.ns_pad + 7) / 8, (long long)sms * 16);
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
+    if (f16 && d <= 256) baseprep_kernel<true, 2><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
+    else if (f16) baseprep_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, direct ? 1 : 0, pl.pitch);
     else baseprep_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(base, nb, 0, 0, d, pl.dh, metric, alpha, beta, sc, bh, so, 0, pl.dh);
     NWK_LAUNCH_CHECK();
   }
@@ -1973,7 +1980,8 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
     // CTAs of this 80-register kernel fit, 8-warp CTAs do not
     const int threads = prep_aside ? 128 : 256;
     long long blocks = std::min<long long>((r1 - r0) / (threads / 32) + 1, (long long)sms * (prep_aside ? 32 : 16));
-    if (f16) baseprep_kernel<true><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, direct ? 1 : 0, pl.pitch);
+    if (f16 && d <= 256) baseprep_kernel<true, 2><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, direct ? 1 : 0, pl.pitch);
+    else if (f16) baseprep_kernel<true><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, direct ? 1 : 0, pl.pitch);
     else baseprep_kernel<false><<<(unsigned)blocks, threads, 0, sp>>>(base, nb, r0, r1, d, pl.dh, metric, alpha, beta, sc, bh, no_sample, 0, pl.dh);
     NWK_LAUNCH_CHECK();
     if (prep_aside) NWK_CUDA(cudaEventRecord(ds->ev_chunk[pi], sp));
