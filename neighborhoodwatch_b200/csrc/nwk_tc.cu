@@ -115,9 +115,8 @@ struct TcParams {
   int metric;
   unsigned long long* prof; // NWK_DEBUG_PROF: per CTA, cycles the MMA issuer spent waiting for (accumulator, operands) and in total, tiles
   int dbg_na;               // NWK_DEBUG_NA = 1: a single resident query buffer even where two fit
-  int dbg;                  // NWK_DEBUG_EPI (timing experiments, results are wrong): 1 = no key passes, 2 = epilogue skips the accumulators
-  int epi_inline;           // four-warpgroup direct-key epilogue: 1 = hits are recorded from the fast path's registers
-                            // (NWK_EPI_INLINE=1, an experiment), 0 = the slow loop that re-reads the hit groups from TMEM
+  int dbg;                  // NWK_DEBUG_EPI (timing experiments, results are wrong): 1 = no key passes, 2 = epilogue skips the accumulators,
+                            // 3 = (four-warpgroup epilogue) the accumulators are read from TMEM and dropped
   float* dump;              // MODE_DUMP: [TQ][TB]
   int dump_qt, dump_t;
   int* err;
@@ -483,36 +482,6 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     p[i] = v;
-}
-
-// Candidate records of one group of 8 accumulator columns (direct keys), taken while the group is still in
-// the fast path's registers.  Called under a DIVERGENT branch by the lanes whose group maximum passed their
-// threshold (one group in ~200 at 384 candidates per query and 2.25M rows), so the accumulator stage can be
-// handed back to the MMA issuer as soon as the fast path is through -- a warp with a hit no longer holds the
-// stage through a second trip to TMEM while the other fifteen wait at the barrier.  Out of line: eight call
-// sites per tile must not grow the hot loop (round 1 lost a factor of 1.4 to instruction-cache misses when
-// everything was inline).  Returns the lane's new count of staged records.
-template <int ASLOTS, int STRIDE>
-__device__ __noinline__ int record_group8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
-                                          float thr, float kscale, long long row_first, long long nb, long long q, int nst,
-                                          unsigned long long* slots, unsigned int* cnt, unsigned long long* log) {
-  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const long long row = row_first + j;
-    if (v[j] > thr && row < nb) {                  // (the zero rows of the tile padding never rank)
-      slots[nst * STRIDE] = (static_cast<unsigned long long>(f2ord(v[j] * kscale)) << 32) | static_cast<unsigned long long>(row);
-      if (++nst == ASLOTS) {
-        // one global atomic reserves log space for the lane's batch of staged records
-        const unsigned int base = atomicAdd(cnt + q, (unsigned int)ASLOTS);
-#pragma unroll
-        for (int i = 0; i < ASLOTS; ++i)
-          if (base + i < LOG_CAP) log[q * LOG_CAP + base + i] = slots[i * STRIDE];
-        nst = 0;
-      }
-    }
-  }
-  return nst;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -985,25 +954,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
             uint32_t(&cur)[16] = (h & 1) ? wb : wa;
             uint32_t(&nxt)[16] = (h & 1) ? wa : wb;
             if (h + 1 < CPW * 2) ptx::tmem_ld_32x16(taddr + c0 * 32 + (h + 1) * 16, nxt);
+            if (p.dbg == 3) continue;                     // (timing experiment: the tile is drained from TMEM, nothing else)
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float m = fmaxf(__uint_as_float(cur[8 * g]), __uint_as_float(cur[8 * g + 1]));
 #pragma unroll
               for (int j = 2; j < 8; j += 2)
                 m = fmaxf(m, fmaxf(__uint_as_float(cur[8 * g + j]), __uint_as_float(cur[8 * g + j + 1])));
-              if (m > thr) {                              // divergent and rare
-                if (p.epi_inline && MODE == MODE_FILTER)
-                  nst = record_group8<ASLOTS, TQ * EPI_WG>(
-                      __uint_as_float(cur[8 * g]), __uint_as_float(cur[8 * g + 1]), __uint_as_float(cur[8 * g + 2]),
-                      __uint_as_float(cur[8 * g + 3]), __uint_as_float(cur[8 * g + 4]), __uint_as_float(cur[8 * g + 5]),
-                      __uint_as_float(cur[8 * g + 6]), __uint_as_float(cur[8 * g + 7]), thr, kscale,
-                      row0 + c0 * 32 + (h * 2 + g) * 8, p.nb, q, nst, reinterpret_cast<unsigned long long*>(s_ab) + etid,
-                      p.cnt, p.log);
-                else
-                  hits |= 1u << (h * 2 + g);              // bit = group of 8 columns, counted from this warp's first column
-              }
+              if (m > thr) hits |= 1u << (h * 2 + g);     // bit = group of 8 columns, counted from this warp's first column
             }
-            __syncwarp();                                 // (the tcgen05 instructions below are warp-collective)
           }
           ptx::tmem_wait_ld();
         }
@@ -1060,7 +1019,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // are still in registers, behind one vote per group: +18 % filter time; four groups per
       // trip with their loads and compare chains interleaved: +9 %; releasing the accumulator
       // stage first and working on hit groups stashed in registers afterwards: +2..4 % -- the
-      // warps' total work per tile, not the slowest warp, is what the tile waits for.) ----
+      // warps' total work per tile, not the slowest warp, is what the tile waits for.  Round 2,
+      // four warpgroups, experiment build on one box: recording the hits from the fast path's
+      // registers under a divergent branch per group, so that no warp makes this second trip to
+      // TMEM: 16.8 -> 18.9 ms, the MMA issuer's wait for the stage 342 -> 811 clk per tile.
+      // What the loop costs there: 16.8 ms with it, 15.0 with no key passing, 14.1 with the
+      // accumulators read and dropped, 14.2 with the epilogue not touching them -- profiles/r02_summary.md.) ----
       if (MODE == MODE_FILTER) {
         uint32_t um = __reduce_or_sync(0xffffffffu, hits);
         unsigned long long* const slots = (EPI_WG > EPI_WG_MAX ? reinterpret_cast<unsigned long long*>(s_ab) : s_app) + etid;
@@ -2058,13 +2022,6 @@ int tc_knn(const float* base, long long nb, const float* query, long long nq, in
   // timing experiments (scripts/gpu_exp.sh builds libnwk_exp.so with -DNWK_EXPERIMENTS); the
   // product library does not read these switches: NWK_DEBUG_EPI makes the results wrong
   if (const char* e = getenv("NWK_DEBUG_EPI")) p.dbg = atoi(e);
-  // Measured (scripts/gpu_r2s.sh, config-5 shard and its squared-L2 twin, two alternating runs each on one box):
-  // filter 16.09 / 16.82 ms with the hits recorded from the fast path's registers against 16.85 / 16.11 ms with
-  // the slow loop over TMEM -- no difference, so the slow path's second trip to TMEM is NOT what holds the
-  // accumulator stage at d = 128.  The loop stays the default: it handles dense hits (small bases, where a
-  // tenth of the columns pass) warp-uniformly, the inline form serialises them lane by lane.
-  p.epi_inline = 0;
-  if (const char* e = getenv("NWK_EPI_INLINE")) p.epi_inline = atoi(e) != 0;                 // experiment switch
   if (const char* e = getenv("NWK_DEBUG_NA")) p.dbg_na = atoi(e);
   if (getenv("NWK_DEBUG_PROF")) {
     NWK_CUDA(cudaMalloc(&d_prof, (size_t)sms * 4 * 8));
