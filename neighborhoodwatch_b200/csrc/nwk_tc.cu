@@ -1022,7 +1022,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       // warps' total work per tile, not the slowest warp, is what the tile waits for.  Round 2,
       // four warpgroups, experiment build on one box: recording the hits from the fast path's
       // registers under a divergent branch per group, so that no warp makes this second trip to
-      // TMEM: 16.8 -> 18.9 ms, the MMA issuer's wait for the stage 342 -> 811 clk per tile.
+      // TMEM: 16.8 -> 18.9 ms.
       // What the loop costs there: 16.8 ms with it, 15.0 with no key passing, 14.1 with the
       // accumulators read and dropped, 14.2 with the epilogue not touching them -- profiles/r02_summary.md.) ----
       if (MODE == MODE_FILTER) {
