@@ -648,6 +648,10 @@ int maxsim_topk(const float* qtok, long long nq, int Tq, const float* docs, long
   // document tile of the exact kernel: TJ = 4 PW tokens as doubles, at most 64 KB (three CTAs per SM)
   int pw = 16;
   while (pw > 2 && (size_t)pw * MSX_WARPS * d * 8 > 64 * 1024) pw >>= 1;
+  if (const char* e = getenv("NWK_MSX_PW")) {                      // experiment switch: tokens per lane (16, 8, 4, 2)
+    const int want = atoi(e);
+    if ((want == 16 || want == 8 || want == 4 || want == 2) && want <= pw) pw = want;
+  }
   const int ex_smem = pw * MSX_WARPS * d * 8 + MSX_WARPS * Tq * 8 + 64;
   if (ex_smem > dev_state()->ms_ex_optin) {
     NWK_CUDA(cudaFuncSetAttribute(ms_exact_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ex_smem));
