@@ -556,7 +556,7 @@ struct Sched {
 // Epilogue warpgroups of a variant.  Direct keys on a single CTA are the short-row kernels, whose
 // epilogue is bound by the latency of its slow path (1.9 hit groups per warp and tile at d = 128,
 // ~600 clk each, issue slots 34 % busy with two warps per scheduler): four warpgroups = four warps
-// per scheduler, each over a quarter of the columns, within 96 registers per thread.
+// per scheduler, each over a quarter of the columns (60 registers per thread in the current build; 102 is the cap).
 template <int MODE, bool CTA2, bool DIRECT>
 __host__ __device__ constexpr int epi_wg() {
   return MODE == MODE_DUMP ? 1 : ((MODE == MODE_FILTER && DIRECT && !CTA2) ? 4 : 2);
@@ -944,7 +944,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CU
       uint32_t hits = 0;
       if (EPI_WG > EPI_WG_MAX) {
         // four warpgroups (direct keys): 64 columns per warp as four 16-column loads, two in flight,
-        // so the whole epilogue fits 96 registers per thread
+        // (60 registers per thread in the current build: the cap of 640 threads is 102)
         if (p.dbg != 2) {
           uint32_t wa[16], wb[16];
           ptx::tmem_ld_32x16(taddr + c0 * 32, wa);
